@@ -1,0 +1,89 @@
+/* llck.h -- C ABI of the B200-native batched KBDM solver (libllck.so).
+ *
+ * The reference (danilomendesdias/llckbdm) is pure Python and has no FFI; the drop-in boundary is its
+ * Python function surface.  This header is what a binding of that surface calls:
+ *
+ *   llck_kbdm_batched   replaces the body of  llckbdm/kbdm.py:19-92  (kbdm: Hankel U matrices :95-130,
+ *                       SVD-reduced GEP :133-212, eigenvector normalisation :215-240, line list :71-92)
+ *                       for a whole ensemble at once, i.e. the serial loop of
+ *                       llckbdm/sampling.py:52-70 (sample_kbdm) becomes ONE call.
+ *
+ * Conventions: plain pointers and sizes only; returns 0 on success, a negative cudaError_t on a CUDA
+ * failure, or a positive LLCK_E_* code on bad arguments; never throws; allocates nothing (the caller
+ * owns every buffer, including the workspace); all device work is issued on `stream`; the call
+ * synchronises that stream (the Jacobi SVD polls a convergence counter once per sweep).
+ * Per-member numerical failures are reported through status[] (the Python wrapper turns them into
+ * numpy.linalg.LinAlgError like np.linalg.inv / scipy.linalg.eig would, kbdm.py:186,192).
+ *
+ * Pointers marked [dev] are device pointers on the current CUDA device, [host] are host pointers.
+ * Complex values are interleaved (re, im) float64 pairs == numpy complex128.
+ */
+#ifndef LLCK_H
+#define LLCK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLCK_VERSION 100
+
+/* argument errors */
+#define LLCK_E_BADARG 1
+#define LLCK_E_WORKSPACE 2
+
+/* per-member status[] values */
+#define LLCK_STATUS_OK 0
+#define LLCK_STATUS_QR_NOCONV 1      /* Hessenberg-QR did not converge (scipy.linalg.eig -> LinAlgError) */
+#define LLCK_STATUS_SINGULAR 2       /* zero singular value among the l kept (np.linalg.inv -> LinAlgError, kbdm.py:186) */
+#define LLCK_STATUS_NONFINITE 3      /* non-finite pole or amplitude */
+#define LLCK_STATUS_SVD_NOCONV 4     /* Jacobi SVD hit the sweep limit */
+
+/* flags */
+#define LLCK_FLAG_DEBUG_KEEP 1       /* keep every intermediate in its own workspace matrix (tests only) */
+
+int llck_version(void);
+
+/* Leading dimension used for every per-member matrix: round_up(max m, 64). */
+int llck_leading_dim(int m_max);
+
+/* Workspace size in bytes for `batch` members with leading dimension ld = llck_leading_dim(max m).
+ * Pure function. flags: 0 or LLCK_FLAG_DEBUG_KEEP. */
+size_t llck_workspace_bytes(int batch, int ld, int flags);
+
+/* Byte offset of debug matrix `which` (0..13) of member 0 inside the workspace (LLCK_FLAG_DEBUG_KEEP layout);
+ * member b is at offset + b * ld*ld*16.
+ * 0:X(=L*S) 1:V 2:Rs 3:Lt 4:T1 5:Ured 6:Hhess 7:Qhess 8:T 9:Z 10:Xev 11:P 12:B 13:W */
+size_t llck_debug_offset(int batch, int ld, int which);
+
+/* Batched KBDM solve.  Member b uses the FID  signals[sig_offset[b] ... ]  (it reads 2*m[b]+p-1 points),
+ * Hankel dimension m[b], kept rank l[b] (1 <= l <= m), shift p >= 1, Tikhonov q >= 0 (kbdm.py:19).
+ *
+ *   line_lists [dev]  float64 [batch][ll_stride]   rows (A, T2, F, PH), l[b] rows per member, eig order (kbdm.py:88-92)
+ *   mu_out     [dev]  complex [batch][mu_stride]   raw poles (optional, may be NULL)
+ *   d_out      [dev]  complex [batch][mu_stride]   complex amplitudes D_k (optional, may be NULL)
+ *   sing_vals  [dev]  float64 [batch][sv_stride]   all m[b] singular values, descending (kbdm.py:68,207)
+ *   n_valid    [dev]  int32   [batch]              rows passing filter_samples (A>1e-6 and T2>0, sampling.py:92-95)
+ *   status     [dev]  int32   [batch]              LLCK_STATUS_*
+ *   info       [host] int32   [4] (optional)       [0]=Jacobi sweeps run, [1]=max QR multishift sweeps, [2..3] reserved
+ */
+int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int32_t* m, const int32_t* l,
+                      int32_t p, double q, double dwell, int32_t batch,
+                      double* line_lists, int64_t ll_stride,
+                      void* mu_out, void* d_out, int64_t mu_stride,
+                      double* sing_vals, int64_t sv_stride,
+                      int32_t* n_valid, int32_t* status,
+                      void* workspace, size_t workspace_bytes, int32_t flags,
+                      void* stream, int32_t* info);
+
+/* Stage-level entry (tests / profiling): one complex GEMM  C = opA(A) * B  through the production kernel.
+ * amode: 0 normal, 1 conj-transpose (A stored K x M), 2 implicit Hankel (A[i,k] = sig[i+k+shift]). All [dev]. */
+int llck_zgemm(int32_t amode, const void* A, int32_t lda, const void* B, int32_t ldb, void* C, int32_t ldc,
+               int32_t M, int32_t N, int32_t K, const void* sig, int32_t shift, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,78 @@
+"""ctypes binding of libllck.so (the C ABI declared in include/llck.h).
+
+The product path has NO CPU fallback: if the CUDA extension is missing or no CUDA device is
+present, every compute entry point raises.  ``load()`` itself only needs the shared object, so the
+CPU test-suite can check that the library loads and exports every declared symbol.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libllck.so")
+
+SYMBOLS = (
+    "llck_version",
+    "llck_leading_dim",
+    "llck_workspace_bytes",
+    "llck_debug_offset",
+    "llck_kbdm_batched",
+    "llck_zgemm",
+)
+
+FLAG_DEBUG_KEEP = 1
+
+STATUS_OK = 0
+STATUS_QR_NOCONV = 1
+STATUS_SINGULAR = 2
+STATUS_NONFINITE = 3
+STATUS_SVD_NOCONV = 4
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libllck.so (built in-tree by ``__graft_entry__.build()``); raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build the CUDA extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()'). llckbdm_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    c_int, c_i64, c_sz, c_vp, c_dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_double
+    lib.llck_version.restype = c_int
+    lib.llck_version.argtypes = []
+    lib.llck_leading_dim.restype = c_int
+    lib.llck_leading_dim.argtypes = [c_int]
+    lib.llck_workspace_bytes.restype = c_sz
+    lib.llck_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.llck_debug_offset.restype = c_sz
+    lib.llck_debug_offset.argtypes = [c_int, c_int, c_int]
+    lib.llck_kbdm_batched.restype = c_int
+    lib.llck_kbdm_batched.argtypes = [
+        c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+        c_int, c_dbl, c_dbl, c_int,
+        c_vp, c_i64,
+        c_vp, c_vp, c_i64,
+        c_vp, c_i64,
+        c_vp, c_vp,
+        c_vp, c_sz, c_int,
+        c_vp, ctypes.POINTER(c_int),
+    ]
+    lib.llck_zgemm.restype = c_int
+    lib.llck_zgemm.argtypes = [c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
+    _lib = lib
+    return lib
+
+
+def check_rc(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError(f"{what}: CUDA error {-rc}")
+    raise ValueError(f"{what}: bad argument (code {rc})")

@@ -1,0 +1,499 @@
+// Batched complex-FP64 nonsymmetric eigensolver for the reduced operator U_red (l x l) -- replaces
+// scipy.linalg.eig / LAPACK zgeev at reference llckbdm/kbdm.py:192.  One CTA per ensemble member:
+//   hessenberg_kernel : Householder reduction H = Q^H U Q, then Q formed by backward accumulation
+//   hqr_kernel        : small-bulge multishift QR (single-shift complex bulges, spacing 2, chased in
+//                       lockstep by one warp each inside a 64x64 shared-memory window; the accumulated
+//                       unitary W is applied to the off-window strips of H and to Z with DMMA GEMMs)
+//   trevc_kernel      : eigenvectors of the triangular Schur factor by column-oriented back substitution
+// Eigenvector scale/phase is irrelevant downstream, so LAPACK's normalisation is not reproduced.
+#pragma once
+#include "common.cuh"
+
+#define E_THREADS 512
+#define E_NWARPS 16
+#define E_W 64          // window size
+#define E_NB 16         // shifts (bulges) per multishift sweep
+#define E_LDW 68        // ld of Hw/Ww in smem (= 4 mod 8)
+#define E_MAT (E_LDW * E_W)
+#define E_TILE (68 * 32)   // strip tile: [68 x 32] (row strips) or [34 x 64] (col strips)
+#define E_LDS 17        // ld of the shift scratch matrix
+#define HQR_SMEM_BYTES ((2 * E_MAT + 2 * E_TILE + E_LDS * E_NB + 64) * 16 + 1024)
+
+// ---------------------------------------------------------------------------------------------
+// Hessenberg reduction + Q formation
+// ---------------------------------------------------------------------------------------------
+// dynamic smem: ldmax * 16 (v) + 512 bytes
+__global__ void __launch_bounds__(E_THREADS, 1) hessenberg_kernel(cplx* H, cplx* Q, long long stride, int ld, const int* lv, cplx* tau_ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* v = reinterpret_cast<cplx*>(smem_raw);
+    double* red = reinterpret_cast<double*>(v + ld);
+    const int b = blockIdx.x, n = lv[b];
+    cplx* Hb = H + (long long)b * stride;
+    cplx* Qb = Q + (long long)b * stride;
+    cplx* tau_b = tau_ws + (long long)b * ld;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int k = 0; k + 2 < n; ++k) {
+        const int len = n - k - 1;
+        cplx* colk = Hb + (long long)ld * k + (k + 1);
+        double part = 0.0;
+        for (int i = 1 + tid; i < len; i += E_THREADS) part += cabs2(colk[i]);
+        const double xnorm2 = block_sum(part, red);
+        const cplx alpha = colk[0];
+        if (xnorm2 == 0.0 && alpha.y == 0.0) {
+            if (tid == 0) tau_b[k] = mkc(0.0, 0.0);
+            __syncthreads();
+            continue;
+        }
+        const double beta = -copysign(sqrt(cabs2(alpha) + xnorm2), alpha.x);
+        const cplx tau = mkc((beta - alpha.x) / beta, -alpha.y / beta);
+        const cplx scale = cdiv(mkc(1.0, 0.0), mkc(alpha.x - beta, alpha.y));
+        __syncthreads();   // everyone has read alpha
+        for (int i = tid; i < len; i += E_THREADS) {
+            if (i == 0) { v[0] = mkc(1.0, 0.0); colk[0] = mkc(beta, 0.0); }
+            else { cplx vv = cmul(colk[i], scale); v[i] = vv; colk[i] = vv; }
+        }
+        if (tid == 0) tau_b[k] = tau;
+        __syncthreads();
+        // left: A[k+1:n, k+1:n] -= conj(tau) v (v^H A)
+        const cplx ctau = cconj(tau);
+        for (int j = k + 1 + warp; j < n; j += E_NWARPS) {
+            cplx* col = Hb + (long long)ld * j + (k + 1);
+            cplx d = mkc(0.0, 0.0);
+            for (int i = lane; i < len; i += 32) d = cfmac(v[i], col[i], d);
+            d = warp_sum(d);
+            const cplx f = cmul(ctau, d);
+            for (int i = lane; i < len; i += 32) col[i] = csub(col[i], cmul(f, v[i]));
+        }
+        __syncthreads();
+        // right: A[0:n, k+1:n] -= tau (A v) v^H
+        for (int i = tid; i < n; i += E_THREADS) {
+            cplx* row = Hb + i + (long long)ld * (k + 1);
+            cplx y0 = mkc(0.0, 0.0), y1 = mkc(0.0, 0.0);
+            int j = 0;
+            for (; j + 1 < len; j += 2) {
+                y0 = cfma(row[(long long)ld * j], v[j], y0);
+                y1 = cfma(row[(long long)ld * (j + 1)], v[j + 1], y1);
+            }
+            if (j < len) y0 = cfma(row[(long long)ld * j], v[j], y0);
+            const cplx ty = cmul(tau, cadd(y0, y1));
+            for (j = 0; j < len; ++j) {
+                cplx* e = row + (long long)ld * j;
+                *e = csub(*e, cmul(ty, cconj(v[j])));
+            }
+        }
+        __syncthreads();
+    }
+    // ---- Q = P_0 P_1 ... P_{n-3} by backward accumulation ----
+    for (long long idx = tid; idx < (long long)ld * n; idx += E_THREADS) {
+        int i = (int)(idx % ld), j = (int)(idx / ld);
+        Qb[idx] = mkc((i == j) ? 1.0 : 0.0, 0.0);
+    }
+    __syncthreads();
+    for (int k = n - 3; k >= 0; --k) {
+        const cplx tau = tau_b[k];
+        if (tau.x == 0.0 && tau.y == 0.0) continue;
+        const int len = n - k - 1;
+        const cplx* colk = Hb + (long long)ld * k + (k + 1);
+        for (int i = tid; i < len; i += E_THREADS) v[i] = (i == 0) ? mkc(1.0, 0.0) : colk[i];
+        __syncthreads();
+        for (int j = k + 1 + warp; j < n; j += E_NWARPS) {
+            cplx* col = Qb + (long long)ld * j + (k + 1);
+            cplx d = mkc(0.0, 0.0);
+            for (int i = lane; i < len; i += 32) d = cfmac(v[i], col[i], d);
+            d = warp_sum(d);
+            const cplx f = cmul(tau, d);
+            for (int i = lane; i < len; i += 32) col[i] = csub(col[i], cmul(f, v[i]));
+        }
+        __syncthreads();
+    }
+    // ---- clear the reflector storage below the subdiagonal ----
+    for (int j = warp; j + 2 < n; j += E_NWARPS) {
+        cplx* col = Hb + (long long)ld * j;
+        for (int i = j + 2 + lane; i < n; i += 32) col[i] = mkc(0.0, 0.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small dense Hessenberg QR in shared memory, executed by ONE warp (all lanes run the same control flow)
+// Hs: n x n upper Hessenberg (ld ldh) -> upper triangular; W (optional, wrows x n, ld ldw) <- W * (rotations)
+// returns number of QR sweeps, or -1 on non-convergence
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool negligible_sub(cplx sub, cplx d0, cplx d1) {
+    const double h = cabs1(sub);
+    if (h <= LLCK_SAFMIN / LLCK_EPS) return true;
+    const double tst = cabs1(d0) + cabs1(d1);
+    return h <= LLCK_EPS * tst;
+}
+
+__device__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, int n, int wrows) {
+    const int lane = threadIdx.x & 31;
+    int ihi = n - 1, its = 0, total = 0;
+    while (ihi >= 0) {
+        int ilo = ihi;
+        while (ilo > 0 && !negligible_sub(Hs[ilo + ldh * (ilo - 1)], Hs[(ilo - 1) + ldh * (ilo - 1)], Hs[ilo + ldh * ilo])) --ilo;
+        if (ilo > 0) {
+            if (lane == 0) Hs[ilo + ldh * (ilo - 1)] = mkc(0.0, 0.0);
+            __syncwarp();
+        }
+        if (ilo == ihi) { --ihi; its = 0; continue; }
+        ++its; ++total;
+        if (its > 300) return -1;
+        cplx sh;
+        if (its % 10 == 0) {
+            cplx d = Hs[ihi + ldh * ihi];
+            sh = mkc(d.x + 0.75 * fabs(Hs[ihi + ldh * (ihi - 1)].x), d.y);
+        } else {
+            cplx a = Hs[(ihi - 1) + ldh * (ihi - 1)], bb = Hs[(ihi - 1) + ldh * ihi];
+            cplx cc = Hs[ihi + ldh * (ihi - 1)], d = Hs[ihi + ldh * ihi];
+            cplx tr2 = cscale(cadd(a, d), 0.5);
+            cplx det = csub(cmul(a, d), cmul(bb, cc));
+            cplx disc = csqrt_(csub(cmul(tr2, tr2), det));
+            cplx e1 = cadd(tr2, disc), e2 = csub(tr2, disc);
+            sh = (cabs2(csub(e1, d)) < cabs2(csub(e2, d))) ? e1 : e2;
+        }
+        for (int k = ilo; k < ihi; ++k) {
+            cplx x, y;
+            if (k == ilo) { x = csub(Hs[ilo + ldh * ilo], sh); y = Hs[(ilo + 1) + ldh * ilo]; }
+            else { x = Hs[k + ldh * (k - 1)]; y = Hs[(k + 1) + ldh * (k - 1)]; }
+            double c; cplx s;
+            givens(x, y, c, s);
+            const cplx cs = cconj(s);
+            __syncwarp();
+            const int c0 = (k > ilo) ? k - 1 : k;
+            for (int col = c0 + lane; col < n; col += 32) {
+                cplx a = Hs[k + ldh * col], bq = Hs[(k + 1) + ldh * col];
+                Hs[k + ldh * col] = cadd(cscale(a, c), cmul(s, bq));
+                Hs[(k + 1) + ldh * col] = csub(cscale(bq, c), cmul(cs, a));
+            }
+            __syncwarp();
+            if (k > ilo && lane == 0) Hs[(k + 1) + ldh * (k - 1)] = mkc(0.0, 0.0);
+            const int r1 = min(k + 2, ihi);
+            for (int row = lane; row <= r1; row += 32) {
+                cplx a = Hs[row + ldh * k], bq = Hs[row + ldh * (k + 1)];
+                Hs[row + ldh * k] = cadd(cscale(a, c), cmul(cs, bq));
+                Hs[row + ldh * (k + 1)] = csub(cscale(bq, c), cmul(s, a));
+            }
+            if (W != nullptr) {
+                for (int row = lane; row < wrows; row += 32) {
+                    cplx a = W[row + ldw * k], bq = W[row + ldw * (k + 1)];
+                    W[row + ldw * k] = cadd(cscale(a, c), cmul(cs, bq));
+                    W[row + ldw * (k + 1)] = csub(cscale(bq, c), cmul(s, a));
+                }
+            }
+            __syncwarp();
+        }
+    }
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply the window transform Ww (64x64 in smem, identity-padded beyond ww) to the off-window strips:
+//   H[ws:we, we:n] <- Ww^H H[ws:we, we:n];  H[0:ws, ws:we] <- H[0:ws, ws:we] Ww;  Z[:, ws:we] <- Z[:, ws:we] Ww
+// all E_THREADS threads participate; tiles: 2 x E_TILE double buffer
+// ---------------------------------------------------------------------------------------------
+__device__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, int n, int ws, int we, const cplx* Ww, cplx* tiles) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int ww = we - ws;
+    // ---- row strip ----
+    {
+        const int ncols = n - we;
+        const int ntiles = (ncols + 31) / 32;
+        auto load = [&](int buf, int tl) {
+            const int c0 = we + tl * 32;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int idx = tid + E_THREADS * r;      // 64 x 32 = 2048
+                int k = idx & 63, j = idx >> 6;
+                bool ok = (k < ww) && (c0 + j < n);
+                const cplx* src = ok ? (Hb + (ws + k) + (long long)ld * (c0 + j)) : Hb;
+                cp_async16(&tiles[buf * E_TILE + k + 68 * j], src, ok);
+            }
+            cp_async_commit();
+        };
+        const int wr = warp >> 1, wc = warp & 1;
+        if (ntiles > 0) load(0, 0);
+        for (int tl = 0; tl < ntiles; ++tl) {
+            const int buf = tl & 1;
+            if (tl + 1 < ntiles) { load(buf ^ 1, tl + 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();
+            const cplx* T = tiles + buf * E_TILE;
+            double acc[1][2][4];
+            zero_acc<1, 2>(acc);
+            warp_zmma<1, 2, true, false>(acc, Ww + E_LDW * (8 * wr), E_LDW, 1, T + 68 * (16 * wc), 1, 68, E_W);
+            const int row = 8 * wr + g;
+            if (row < ww) {
+                const int c0 = we + tl * 32 + 16 * wc;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    int c = c0 + 8 * j + 2 * t;
+                    if (c < n) Hb[(ws + row) + (long long)ld * c] = mkc(acc[0][j][0], acc[0][j][2]);
+                    if (c + 1 < n) Hb[(ws + row) + (long long)ld * (c + 1)] = mkc(acc[0][j][1], acc[0][j][3]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- column strips: H rows [0, ws) then Z rows [0, n) ----
+    for (int which = 0; which < 2; ++which) {
+        cplx* Mb = which ? Zb : Hb;
+        const int nrows = which ? n : ws;
+        const int ntiles = (nrows + 31) / 32;
+        auto load = [&](int buf, int tl) {
+            const int r0 = tl * 32;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int idx = tid + E_THREADS * r;      // 32 x 64
+                int i = idx & 31, k = idx >> 5;
+                bool ok = (r0 + i < nrows) && (k < ww);
+                const cplx* src = ok ? (Mb + (r0 + i) + (long long)ld * (ws + k)) : Mb;
+                cp_async16(&tiles[buf * E_TILE + i + 34 * k], src, ok);
+            }
+            cp_async_commit();
+        };
+        const int wr = warp >> 2, wc = warp & 3;
+        if (ntiles > 0) load(0, 0);
+        for (int tl = 0; tl < ntiles; ++tl) {
+            const int buf = tl & 1;
+            if (tl + 1 < ntiles) { load(buf ^ 1, tl + 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();
+            const cplx* T = tiles + buf * E_TILE;
+            double acc[1][2][4];
+            zero_acc<1, 2>(acc);
+            warp_zmma<1, 2, false, false>(acc, T + 8 * wr, 1, 34, Ww + E_LDW * (16 * wc), 1, E_LDW, E_W);
+            const int row = tl * 32 + 8 * wr + g;
+            if (row < nrows) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    int c = 16 * wc + 8 * j + 2 * t;
+                    if (c < ww) Mb[row + (long long)ld * (ws + c)] = mkc(acc[0][j][0], acc[0][j][2]);
+                    if (c + 1 < ww) Mb[row + (long long)ld * (ws + c + 1)] = mkc(acc[0][j][1], acc[0][j][3]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int block_max_int(int v, int* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = __reduce_max_sync(0xffffffffu, v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    int r = (lane < E_NWARPS) ? scratch[lane] : -2147483647;
+    r = __reduce_max_sync(0xffffffffu, r);
+    return r;
+}
+
+// status: 0 ok, 1 = QR did not converge
+__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* Hw = reinterpret_cast<cplx*>(smem_raw);
+    cplx* Ww = Hw + E_MAT;
+    cplx* tiles = Ww + E_MAT;
+    cplx* Hs = tiles + 2 * E_TILE;            // E_LDS x E_NB
+    cplx* shifts = Hs + E_LDS * E_NB;         // E_NB (+ padding to 64)
+    int* iscr = reinterpret_cast<int*>(shifts + 64);   // 64 ints
+    const int b = blockIdx.x, n = lv[b];
+    cplx* Hb = H + (long long)b * stride;
+    cplx* Zb = Z + (long long)b * stride;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    int ihi = n - 1, its = 0, nsweeps = 0;
+    bool failed = false;
+    while (ihi >= 0) {
+        __syncthreads();
+        // ---- deflation scan: largest k in [1, ihi] with negligible H[k,k-1] ----
+        int cand = 0;
+        for (int k = ihi - tid; k >= 1; k -= E_THREADS) {
+            if (negligible_sub(Hb[k + (long long)ld * (k - 1)], Hb[(k - 1) + (long long)ld * (k - 1)], Hb[k + (long long)ld * k])) { cand = k; break; }
+        }
+        const int ilo = block_max_int(cand, iscr);
+        if (ilo > 0 && tid == 0) Hb[ilo + (long long)ld * (ilo - 1)] = mkc(0.0, 0.0);
+        if (ilo == ihi) { --ihi; its = 0; continue; }
+        const int size = ihi - ilo + 1;
+        if (size <= E_W) {
+            // ---- whole active block fits in the window: finish it in shared memory ----
+            for (int idx = tid; idx < E_W * E_W; idx += E_THREADS) {
+                int r = idx & 63, c = idx >> 6;
+                cplx hv = mkc(0.0, 0.0);
+                if (r < size && c < size) hv = Hb[(ilo + r) + (long long)ld * (ilo + c)];
+                Hw[r + E_LDW * c] = hv;
+                Ww[r + E_LDW * c] = mkc(r == c ? 1.0 : 0.0, 0.0);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int r = warp_small_hqr(Hw, E_LDW, Ww, E_LDW, size, size);
+                if (lane == 0) iscr[32] = r;
+            }
+            __syncthreads();
+            if (iscr[32] < 0) { failed = true; break; }
+            for (int idx = tid; idx < size * size; idx += E_THREADS) {
+                int r = idx % size, c = idx / size;
+                Hb[(ilo + r) + (long long)ld * (ilo + c)] = Hw[r + E_LDW * c];
+            }
+            apply_window_transform(Hb, Zb, ld, n, ilo, ihi + 1, Ww, tiles);
+            ihi = ilo - 1; its = 0;
+            continue;
+        }
+        ++its;
+        if (its > 60) { failed = true; break; }
+        // ---- shifts: eigenvalues of the trailing E_NB x E_NB block ----
+        if (its % 6 == 0) {
+            if (tid < E_NB) {
+                cplx d = Hb[(ihi - tid) + (long long)ld * (ihi - tid)];
+                cplx sub = Hb[(ihi - tid) + (long long)ld * (ihi - tid - 1)];
+                shifts[tid] = mkc(d.x + 0.75 * cabs_(sub), d.y);
+            }
+            __syncthreads();
+        } else {
+            for (int idx = tid; idx < E_NB * E_NB; idx += E_THREADS) {
+                int r = idx % E_NB, c = idx / E_NB;
+                cplx hv = Hb[(ihi - E_NB + 1 + r) + (long long)ld * (ihi - E_NB + 1 + c)];
+                if (r > c + 1) hv = mkc(0.0, 0.0);
+                Hs[r + E_LDS * c] = hv;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int r = warp_small_hqr(Hs, E_LDS, nullptr, 0, E_NB, 0);
+                if (lane == 0) iscr[32] = r;
+                __syncwarp();
+                if (lane < E_NB) shifts[lane] = Hs[lane + E_LDS * lane];
+            }
+            __syncthreads();
+            if (iscr[32] < 0) { failed = true; break; }
+        }
+        // ---- one multishift sweep over [ilo, ihi] ----
+        ++nsweeps;
+        int tstep = 0;
+        while (true) {
+            const int p_last = ilo - 1 - 2 * (E_NB - 1) + tstep;
+            if (p_last > ihi - 2) break;
+            const int p_top = max(ilo - 1, p_last);
+            const int p0 = ilo - 1 + tstep;
+            const int ws = max(ilo, p_top);
+            const int we = min(ws + E_W, ihi + 1);
+            const int T = (we == ihi + 1) ? ((ihi - 2) - p_last + 1) : (we - 3 - p0);
+            const int ww = we - ws;
+            __syncthreads();
+            for (int idx = tid; idx < E_W * E_W; idx += E_THREADS) {
+                int r = idx & 63, c = idx >> 6;
+                cplx hv = mkc(0.0, 0.0);
+                if (r < ww && c < ww) hv = Hb[(ws + r) + (long long)ld * (ws + c)];
+                Hw[r + E_LDW * c] = hv;
+                Ww[r + E_LDW * c] = mkc(r == c ? 1.0 : 0.0, 0.0);
+            }
+            __syncthreads();
+            for (int step = 0; step < T; ++step) {
+                const int p = ilo - 1 - 2 * warp + tstep + step;     // this warp's bulge
+                const bool active = (p >= ilo - 1) && (p <= ihi - 2);
+                double c = 1.0; cplx s = mkc(0.0, 0.0);
+                if (active) {
+                    cplx x, y;
+                    if (p == ilo - 1) { x = csub(Hw[(ilo - ws) + E_LDW * (ilo - ws)], shifts[warp]); y = Hw[(ilo + 1 - ws) + E_LDW * (ilo - ws)]; }
+                    else { x = Hw[(p + 1 - ws) + E_LDW * (p - ws)]; y = Hw[(p + 2 - ws) + E_LDW * (p - ws)]; }
+                    givens(x, y, c, s);
+                    const cplx cs = cconj(s);
+                    const int r = p + 1 - ws;
+                    const int c0 = max(p - ws, 0);
+                    __syncwarp();
+                    for (int col = c0 + lane; col < ww; col += 32) {
+                        cplx a = Hw[r + E_LDW * col], bq = Hw[(r + 1) + E_LDW * col];
+                        Hw[r + E_LDW * col] = cadd(cscale(a, c), cmul(s, bq));
+                        Hw[(r + 1) + E_LDW * col] = csub(cscale(bq, c), cmul(cs, a));
+                    }
+                    __syncwarp();
+                    if (p >= ilo && lane == 0) Hw[(r + 1) + E_LDW * (p - ws)] = mkc(0.0, 0.0);
+                }
+                __syncthreads();
+                if (active) {
+                    const cplx cs = cconj(s);
+                    const int k = p + 1 - ws;
+                    const int r1 = min(p + 3, ihi) - ws + 1;
+                    for (int row = lane; row < r1; row += 32) {
+                        cplx a = Hw[row + E_LDW * k], bq = Hw[row + E_LDW * (k + 1)];
+                        Hw[row + E_LDW * k] = cadd(cscale(a, c), cmul(cs, bq));
+                        Hw[row + E_LDW * (k + 1)] = csub(cscale(bq, c), cmul(s, a));
+                    }
+                    for (int row = lane; row < ww; row += 32) {
+                        cplx a = Ww[row + E_LDW * k], bq = Ww[row + E_LDW * (k + 1)];
+                        Ww[row + E_LDW * k] = cadd(cscale(a, c), cmul(cs, bq));
+                        Ww[row + E_LDW * (k + 1)] = csub(cscale(bq, c), cmul(s, a));
+                    }
+                }
+                __syncthreads();
+            }
+            for (int idx = tid; idx < ww * ww; idx += E_THREADS) {
+                int r = idx % ww, c = idx / ww;
+                Hb[(ws + r) + (long long)ld * (ws + c)] = Hw[r + E_LDW * c];
+            }
+            apply_window_transform(Hb, Zb, ld, n, ws, we, Ww, tiles);
+            tstep += T;
+        }
+    }
+    if (tid == 0) {
+        if (failed) atomicMax(&status[b], 1);
+        if (sweeps_out) sweeps_out[b] = nsweeps;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// eigenvectors of upper-triangular T (in H storage): X upper triangular, T X = X diag(T)
+// dynamic smem: ld*16 (tcol) + ld*8 (smin) + 512
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(E_THREADS, 1) trevc_kernel(const cplx* Tm, cplx* X, long long stride, int ld, const int* lv) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* tcol = reinterpret_cast<cplx*>(smem_raw);
+    cplx* tdiag = tcol + ld;
+    double* red = reinterpret_cast<double*>(tdiag + ld);
+    const int b = blockIdx.x, n = lv[b];
+    const cplx* Tb = Tm + (long long)b * stride;
+    cplx* Xb = X + (long long)b * stride;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double smlnum = LLCK_SAFMIN * ((double)n / LLCK_EPS);
+
+    for (int k = warp; k < n; k += E_NWARPS) {
+        const cplx* tc = Tb + (long long)ld * k;
+        cplx* xc = Xb + (long long)ld * k;
+        for (int i = lane; i < n; i += 32) xc[i] = (i < k) ? cneg(tc[i]) : mkc(i == k ? 1.0 : 0.0, 0.0);
+    }
+    for (int i = tid; i < n; i += E_THREADS) tdiag[i] = Tb[i + (long long)ld * i];
+    __syncthreads();
+    for (int j = n - 2; j >= 0; --j) {
+        const cplx tjj = tdiag[j];
+        // divisions on row j, and stage column j of T
+        for (int k = j + 1 + tid; k < n; k += E_THREADS) {
+            const cplx tkk = tdiag[k];
+            cplx d = csub(tjj, tkk);
+            const double smin = fmax(LLCK_EPS * cabs1(tkk), smlnum);
+            if (cabs1(d) < smin) d = mkc(smin, 0.0);
+            cplx* e = Xb + j + (long long)ld * k;
+            *e = cdiv(*e, d);
+        }
+        for (int i = tid; i < j; i += E_THREADS) tcol[i] = Tb[i + (long long)ld * j];
+        __syncthreads();
+        if (j > 0) {
+            for (int k = j + 1 + warp; k < n; k += E_NWARPS) {
+                cplx* xc = Xb + (long long)ld * k;
+                const cplx xjk = xc[j];
+                for (int i = lane; i < j; i += 32) xc[i] = csub(xc[i], cmul(xjk, tcol[i]));
+            }
+        }
+        __syncthreads();
+    }
+    // normalise each eigenvector to unit max-|.|_1 entry (keeps downstream products well scaled)
+    for (int k = warp; k < n; k += E_NWARPS) {
+        cplx* xc = Xb + (long long)ld * k;
+        double mx = 0.0;
+        for (int i = lane; i <= k; i += 32) mx = fmax(mx, cabs1(xc[i]));
+        mx = warp_max(mx);
+        if (mx > 0.0 && isfinite(mx)) {
+            const double sc = 1.0 / mx;
+            for (int i = lane; i <= k; i += 32) xc[i] = cscale(xc[i], sc);
+        }
+    }
+    (void)red;
+}

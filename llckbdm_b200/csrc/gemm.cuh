@@ -1,0 +1,178 @@
+// Batched complex-FP64 GEMM on DMMA tensor cores, one launch for a whole ensemble of members with
+// per-member sizes.  C_b = opA(A_b) * B_b, column-major, 64x64 CTA tiles, K chunks of 16 staged with
+// cp.async double buffering.
+//
+// A operand modes:
+//   A_NORMAL : A_b is M x K column-major (lda)
+//   A_CONJT  : A_b is stored K x M column-major (lda); the product uses conj(A_b)^T  (L^H * X)
+//   A_HANKEL : A_b[i,k] = c_b[i + k + shift] -- the Hankel matrix U^shift is NEVER materialised: the
+//              member's FID slice is bulk-copied (TMA, cp.async.bulk) into shared memory once per CTA
+//              and every A fragment is read from it as a sliding window.
+//              (reference: llckbdm/kbdm.py:95-130 builds the m x m matrices row by row on the host)
+#pragma once
+#include "common.cuh"
+
+enum { A_NORMAL = 0, A_CONJT = 1, A_HANKEL = 2 };
+
+struct GemmParams {
+    const cplx* A; long long strideA; int lda;       // unused for A_HANKEL
+    const cplx* B; long long strideB; int ldb;
+    cplx* C;       long long strideC; int ldc;
+    const int* Mv; const int* Nv; const int* Kv;     // per-member dims (device arrays, length batch)
+    // Hankel source
+    const cplx* sig; const long long* sig_off; int shift;
+};
+
+#define G_BM 64
+#define G_BN 64
+#define G_BK 16
+#define G_LDA_N 66   // normal A tile: As[i + 66*k]   (ld = 2 mod 8: conflict-free DMMA A-fragment reads)
+#define G_LDA_T 20   // conj-trans A tile: As[k + 20*i] (ld = 4 mod 8)
+#define G_LDB 20     // B tile: Bs[k + 20*j]
+#define G_A_ELEMS 1280
+#define G_B_ELEMS 1280
+#define G_SIG_MAX 4352  // max Hankel slice (complex) kept in smem: supports m up to 2048+
+
+template <int AMODE>
+__global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* smem = reinterpret_cast<cplx*>(smem_raw);
+    const int b = blockIdx.z;
+    const int M = p.Mv[b], N = p.Nv[b], K = p.Kv[b];
+    const int row0 = blockIdx.x * G_BM, col0 = blockIdx.y * G_BN;
+    if (row0 >= M || col0 >= N) return;
+
+    cplx* As[2];
+    cplx* Bs[2];
+    cplx* sigs = nullptr;
+    if (AMODE == A_HANKEL) {
+        Bs[0] = smem; Bs[1] = smem + G_B_ELEMS;
+        sigs = smem + 2 * G_B_ELEMS;
+        As[0] = As[1] = nullptr;
+    } else {
+        As[0] = smem; As[1] = smem + G_A_ELEMS;
+        Bs[0] = smem + 2 * G_A_ELEMS; Bs[1] = Bs[0] + G_B_ELEMS;
+    }
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int wr = warp >> 1, wc = warp & 1;   // warp tile: rows 16*wr.., cols 32*wc..
+
+    const cplx* Ag = (AMODE == A_HANKEL) ? nullptr : p.A + (long long)b * p.strideA;
+    const cplx* Bg = p.B + (long long)b * p.strideB;
+    cplx* Cg = p.C + (long long)b * p.strideC;
+
+    __shared__ uint64_t bar;
+    int nsig = 0;
+    if (AMODE == A_HANKEL) {
+        // slice needed by this CTA: c[shift + row0 .. shift + row0 + 64 + K - 2]
+        nsig = min(G_BM, M - row0) + K - 1;
+        const cplx* src = p.sig + p.sig_off[b] + p.shift + row0;
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) tma_load_1d(sigs, src, (uint32_t)nsig * 16u, &bar);
+        // zero the tail so out-of-range rows/k read finite data (their products are discarded or hit zero B rows)
+        for (int i = nsig + tid; i < G_BM + ((K + G_BK - 1) / G_BK) * G_BK + 8; i += 256)
+            if (i < G_SIG_MAX) sigs[i] = mkc(0.0, 0.0);
+    }
+
+    auto load_tiles = [&](int buf, int k0) {
+        if (AMODE == A_NORMAL) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int idx = tid + 256 * r;
+                int i = idx & 63, k = idx >> 6;
+                bool ok = (row0 + i < M) && (k0 + k < K);
+                const cplx* src = ok ? (Ag + (row0 + i) + (long long)p.lda * (k0 + k)) : Ag;
+                cp_async16(&As[buf][i + G_LDA_N * k], src, ok);
+            }
+        } else if (AMODE == A_CONJT) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int idx = tid + 256 * r;
+                int k = idx & 15, i = idx >> 4;
+                bool ok = (row0 + i < M) && (k0 + k < K);
+                const cplx* src = ok ? (Ag + (k0 + k) + (long long)p.lda * (row0 + i)) : Ag;
+                cp_async16(&As[buf][k + G_LDA_T * i], src, ok);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int idx = tid + 256 * r;
+            int k = idx & 15, j = idx >> 4;
+            bool ok = (col0 + j < N) && (k0 + k < K);
+            const cplx* src = ok ? (Bg + (k0 + k) + (long long)p.ldb * (col0 + j)) : Bg;
+            cp_async16(&Bs[buf][k + G_LDB * j], src, ok);
+        }
+        cp_async_commit();
+    };
+
+    double acc[2][4][4];
+    zero_acc<2, 4>(acc);
+
+    const int nk = (K + G_BK - 1) / G_BK;
+    load_tiles(0, 0);
+    if (AMODE == A_HANKEL) {
+        mbar_wait(&bar, 0);
+        __syncthreads();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) {
+            load_tiles(buf ^ 1, (kt + 1) * G_BK);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (AMODE == A_NORMAL) {
+            warp_zmma<2, 4, false, false>(acc, As[buf] + 16 * wr, 1, G_LDA_N, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
+        } else if (AMODE == A_CONJT) {
+            warp_zmma<2, 4, true, false>(acc, As[buf] + G_LDA_T * (16 * wr), G_LDA_T, 1, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
+        } else {
+            warp_zmma<2, 4, false, false>(acc, sigs + 16 * wr + kt * G_BK, 1, 1, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
+        }
+        __syncthreads();
+    }
+
+    // store
+    const int lane = tid & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = row0 + 16 * wr + 8 * i + g;
+        if (r >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = col0 + 32 * wc + 8 * j + 2 * t;
+            if (c < N) Cg[r + (long long)p.ldc * c] = mkc(acc[i][j][0], acc[i][j][2]);
+            if (c + 1 < N) Cg[r + (long long)p.ldc * (c + 1)] = mkc(acc[i][j][1], acc[i][j][3]);
+        }
+    }
+}
+
+static inline size_t zgemm_smem_bytes(int amode, int Kmax) {
+    if (amode == A_HANKEL) return (size_t)(2 * G_B_ELEMS + G_SIG_MAX) * sizeof(cplx);
+    return (size_t)(2 * G_A_ELEMS + 2 * G_B_ELEMS) * sizeof(cplx);
+}
+
+// Launch: grid = (ceil(Mmax/64), ceil(Nmax/64), batch)
+static inline cudaError_t zgemm_batched(int amode, const GemmParams& p, int Mmax, int Nmax, int Kmax, int batch,
+                                        cudaStream_t stream) {
+    if (batch <= 0 || Mmax <= 0 || Nmax <= 0) return cudaSuccess;
+    dim3 grid((Mmax + G_BM - 1) / G_BM, (Nmax + G_BN - 1) / G_BN, batch);
+    size_t smem = zgemm_smem_bytes(amode, Kmax);
+    cudaError_t e;
+    if (amode == A_NORMAL) {
+        e = cudaFuncSetAttribute(zgemm_batched_kernel<A_NORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        zgemm_batched_kernel<A_NORMAL><<<grid, 256, smem, stream>>>(p);
+    } else if (amode == A_CONJT) {
+        e = cudaFuncSetAttribute(zgemm_batched_kernel<A_CONJT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        zgemm_batched_kernel<A_CONJT><<<grid, 256, smem, stream>>>(p);
+    } else {
+        if (64 + Kmax + 32 > G_SIG_MAX) return cudaErrorInvalidValue;
+        e = cudaFuncSetAttribute(zgemm_batched_kernel<A_HANKEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        zgemm_batched_kernel<A_HANKEL><<<grid, 256, smem, stream>>>(p);
+    }
+    return cudaGetLastError();
+}

@@ -1,0 +1,305 @@
+// C-ABI of libllck.so: orchestration of the batched KBDM solve (see include/llck.h).
+// Pipeline per ensemble member (reference llckbdm/kbdm.py:19-92, 133-240):
+//   X <- Hankel(U^{p-1});  block-Jacobi SVD  X = L S, V = R                    (kbdm.py:166)
+//   Rs = R_l g^{-1/2},  Lt = L_l g^{-1/2}   (g = s or s + q^2/s)                (kbdm.py:171-186)
+//   T1 = U^p Rs (implicit Hankel GEMM);  Ured = Lt^H T1                         (kbdm.py:189)
+//   Ured = Q H Q^H -> Z T Z^H (Hessenberg + multishift QR);  Xev = trevc(T)     (kbdm.py:192)
+//   P = Z Xev;  B = Rs P                                                        (kbdm.py:198)
+//   W = U0 B (implicit Hankel GEMM);  N_k = sum_i B_ik W_ik;  D_k = W_0k^2/N_k  (kbdm.py:215-240, 71-75)
+//   (A, T2, F, PH) from D_k and mu_k = T_kk                                      (kbdm.py:78-92)
+#include "../../include/llck.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "svd.cuh"
+#include "eig.cuh"
+#include <stdio.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return -(int)e_; } while (0)
+
+// ---- epilogue: one warp per eigen-pair ------------------------------------------------------------
+__global__ void __launch_bounds__(256) epilogue_kernel(const cplx* Bm, const cplx* Wm, const cplx* Tm, long long stride, int ld,
+                                                       const int* mv, const int* lv, double dwell,
+                                                       double* line_lists, long long ll_stride, cplx* mu_out, cplx* d_out,
+                                                       long long mu_stride, int* n_valid, int* status) {
+    const int b = blockIdx.y;
+    const int m = mv[b], l = lv[b];
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= l) return;
+    const cplx* bc = Bm + (long long)b * stride + (long long)ld * k;
+    const cplx* wc = Wm + (long long)b * stride + (long long)ld * k;
+    cplx nk = mkc(0.0, 0.0);
+    for (int i = lane; i < m; i += 32) nk = cfma(bc[i], wc[i], nk);   // bilinear, NO conjugate (kbdm.py:232)
+    nk = warp_sum(nk);
+    if (lane == 0) {
+        const cplx w0 = wc[0];
+        const cplx D = cdiv(cmul(w0, w0), nk);
+        const cplx mu = Tm[(long long)b * stride + k + (long long)ld * k];
+        const double A = hypot(D.x, D.y);
+        const double PH = atan2(D.y, D.x);
+        const double arg = atan2(mu.y, mu.x);
+        const double lnabs = log(hypot(mu.x, mu.y));
+        const double F = arg / (dwell * 6.283185307179586476925286766559);
+        const double T2 = -dwell / lnabs;
+        double* row = line_lists + (long long)b * ll_stride + 4 * k;
+        row[0] = A; row[1] = T2; row[2] = F; row[3] = PH;
+        if (mu_out) mu_out[(long long)b * mu_stride + k] = mu;
+        if (d_out) d_out[(long long)b * mu_stride + k] = D;
+        if (A > 1e-6 && T2 > 0.0) atomicAdd(&n_valid[b], 1);
+        if (!isfinite(A) || !isfinite(mu.x) || !isfinite(mu.y)) atomicMax(&status[b], LLCK_STATUS_NONFINITE);
+    }
+}
+
+__global__ void mark_unconverged_kernel(const int* done, int* status, int batch) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch && !done[b]) atomicMax(&status[b], LLCK_STATUS_SVD_NOCONV);
+}
+
+// ---- workspace layout -----------------------------------------------------------------------------
+struct WsLayout {
+    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, mats, total;
+    int nmats;
+};
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+static WsLayout ws_layout(int batch, int ld, int flags) {
+    WsLayout L;
+    size_t o = 0;
+    L.mv = o; o = al256(o + sizeof(int) * batch);
+    L.lv = o; o = al256(o + sizeof(int) * batch);
+    L.nbv = o; o = al256(o + sizeof(int) * batch);
+    L.done = o; o = al256(o + sizeof(int) * batch);
+    L.n_active = o; o = al256(o + 256);
+    L.hqr_sweeps = o; o = al256(o + sizeof(int) * batch);
+    L.perm = o; o = al256(o + sizeof(int) * (size_t)batch * ld);
+    L.sig_off = o; o = al256(o + sizeof(long long) * batch);
+    L.sweep_off = o; o = al256(o + sizeof(unsigned long long) * batch);
+    L.tau = o; o = al256(o + sizeof(cplx) * (size_t)batch * ld);
+    L.mats = o;
+    L.nmats = (flags & LLCK_FLAG_DEBUG_KEEP) ? 14 : 6;
+    o += (size_t)L.nmats * batch * ld * ld * sizeof(cplx);
+    L.total = o;
+    return L;
+}
+
+extern "C" {
+
+int llck_version(void) { return LLCK_VERSION; }
+
+int llck_leading_dim(int m_max) { return ((m_max + 63) / 64) * 64; }
+
+size_t llck_workspace_bytes(int batch, int ld, int flags) {
+    if (batch <= 0 || ld <= 0) return 0;
+    return ws_layout(batch, ld, flags).total;
+}
+
+size_t llck_debug_offset(int batch, int ld, int which) {
+    WsLayout L = ws_layout(batch, ld, LLCK_FLAG_DEBUG_KEEP);
+    return L.mats + (size_t)which * batch * ld * ld * sizeof(cplx);
+}
+
+int llck_zgemm(int32_t amode, const void* A, int32_t lda, const void* B, int32_t ldb, void* C, int32_t ldc,
+               int32_t M, int32_t N, int32_t K, const void* sig, int32_t shift, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int* dims = nullptr;
+    long long* off = nullptr;
+    CK(cudaMalloc(&dims, 3 * sizeof(int)));
+    CK(cudaMalloc(&off, sizeof(long long)));
+    int h[3] = {M, N, K};
+    long long z = 0;
+    CK(cudaMemcpyAsync(dims, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(off, &z, sizeof(z), cudaMemcpyHostToDevice, st));
+    GemmParams p;
+    p.A = (const cplx*)A; p.strideA = 0; p.lda = lda;
+    p.B = (const cplx*)B; p.strideB = 0; p.ldb = ldb;
+    p.C = (cplx*)C; p.strideC = 0; p.ldc = ldc;
+    p.Mv = dims; p.Nv = dims + 1; p.Kv = dims + 2;
+    p.sig = (const cplx*)sig; p.sig_off = off; p.shift = shift;
+    cudaError_t e = zgemm_batched(amode, p, M, N, K, 1, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(dims); cudaFree(off);
+    if (e != cudaSuccess) return -(int)e;
+    if (e2 != cudaSuccess) return -(int)e2;
+    return 0;
+}
+
+int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int32_t* m, const int32_t* l,
+                      int32_t p, double q, double dwell, int32_t batch,
+                      double* line_lists, int64_t ll_stride,
+                      void* mu_out, void* d_out, int64_t mu_stride,
+                      double* sing_vals, int64_t sv_stride,
+                      int32_t* n_valid, int32_t* status,
+                      void* workspace, size_t workspace_bytes, int32_t flags,
+                      void* stream, int32_t* info) {
+    if (!signals || !sig_offset || !m || !l || !line_lists || !sing_vals || !n_valid || !status || !workspace) return LLCK_E_BADARG;
+    if (batch <= 0 || p < 1 || q < 0.0) return LLCK_E_BADARG;
+    int mmax = 0, lmax = 0;
+    for (int b = 0; b < batch; ++b) {
+        if (m[b] < 1 || l[b] < 1 || l[b] > m[b]) return LLCK_E_BADARG;
+        if (m[b] > mmax) mmax = m[b];
+        if (l[b] > lmax) lmax = l[b];
+        if (ll_stride < 4 * (int64_t)l[b] || sv_stride < m[b]) return LLCK_E_BADARG;
+        if ((mu_out || d_out) && mu_stride < l[b]) return LLCK_E_BADARG;
+    }
+    const int ld = llck_leading_dim(mmax);
+    if (ld > 2048) return LLCK_E_BADARG;
+    const WsLayout L = ws_layout(batch, ld, flags);
+    if (workspace_bytes < L.total) return LLCK_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    int* d_mv = (int*)(ws + L.mv);
+    int* d_lv = (int*)(ws + L.lv);
+    int* d_nbv = (int*)(ws + L.nbv);
+    int* d_done = (int*)(ws + L.done);
+    int* d_nact = (int*)(ws + L.n_active);
+    int* d_hqrs = (int*)(ws + L.hqr_sweeps);
+    int* d_perm = (int*)(ws + L.perm);
+    long long* d_soff = (long long*)(ws + L.sig_off);
+    unsigned long long* d_swoff = (unsigned long long*)(ws + L.sweep_off);
+    cplx* d_tau = (cplx*)(ws + L.tau);
+    cplx* mats = (cplx*)(ws + L.mats);
+    const long long stride = (long long)ld * ld;
+    const bool dbg = (flags & LLCK_FLAG_DEBUG_KEEP) != 0;
+    auto mat = [&](int i) { return mats + (size_t)i * batch * stride; };
+    // buffer assignment (production aliases dead buffers; debug keeps all 14)
+    cplx *bX, *bV, *bRs, *bLt, *bT1, *bH, *bZ, *bXev, *bP, *bB, *bW;
+    if (dbg) { bX = mat(0); bV = mat(1); bRs = mat(2); bLt = mat(3); bT1 = mat(4); bH = mat(8); bZ = mat(9); bXev = mat(10); bP = mat(11); bB = mat(12); bW = mat(13); }
+    else     { bX = mat(0); bV = mat(1); bRs = mat(2); bLt = mat(3); bT1 = mat(0); bH = mat(1); bZ = mat(3); bXev = mat(0); bP = mat(4); bB = mat(5); bW = mat(0); }
+
+    // ---- metadata ----
+    int* h_nb = (int*)malloc(sizeof(int) * batch);
+    if (!h_nb) return LLCK_E_BADARG;
+    int nbmax = 2;
+    for (int b = 0; b < batch; ++b) {
+        int nb = (m[b] + J_B - 1) / J_B;
+        if (nb < 2) nb = 2;
+        if (nb & 1) ++nb;
+        h_nb[b] = nb;
+        if (nb > nbmax) nbmax = nb;
+    }
+    cudaError_t e;
+    e = cudaMemcpyAsync(d_mv, m, sizeof(int) * batch, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_lv, l, sizeof(int) * batch, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_nbv, h_nb, sizeof(int) * batch, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_soff, sig_offset, sizeof(long long) * batch, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    free(h_nb);
+    if (e != cudaSuccess) return -(int)e;
+    CK(cudaMemsetAsync(d_done, 0, sizeof(int) * batch, st));
+    CK(cudaMemsetAsync(d_swoff, 0, sizeof(unsigned long long) * batch, st));
+    CK(cudaMemsetAsync(status, 0, sizeof(int) * batch, st));
+    CK(cudaMemsetAsync(n_valid, 0, sizeof(int) * batch, st));
+    CK(cudaMemsetAsync(d_hqrs, 0, sizeof(int) * batch, st));
+
+    // ---- SVD of U^{p-1} ----
+    {
+        dim3 grid(256, batch);
+        svd_init_kernel<<<grid, 256, 0, st>>>(bX, bV, stride, ld, d_mv, d_nbv, (const cplx*)signals, d_soff, p - 1);
+        CK(cudaGetLastError());
+    }
+    CK(cudaFuncSetAttribute(jacobi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, J_SMEM_BYTES));
+    JacobiParams jp;
+    jp.X = bX; jp.V = bV; jp.stride = stride; jp.ld = ld; jp.mv = d_mv; jp.nbv = d_nbv;
+    jp.sweep_off = d_swoff; jp.done = d_done; jp.tol2 = 1e-28;
+    int sweeps_run = 0;
+    const int max_sweeps = 30;
+    int h_active = batch;
+    for (int sweep = 0; sweep < max_sweeps && h_active > 0; ++sweep) {
+        for (int r = 0; r < nbmax - 1; ++r) {
+            jp.round = r;
+            dim3 grid(nbmax / 2, batch);
+            jacobi_step_kernel<<<grid, 256, J_SMEM_BYTES, st>>>(jp);
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemsetAsync(d_nact, 0, sizeof(int), st));
+        jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, d_nact, batch, 1e-14);
+        CK(cudaMemcpyAsync(&h_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ++sweeps_run;
+    }
+    if (h_active > 0) {
+        mark_unconverged_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_done, status, batch);
+        CK(cudaGetLastError());
+    }
+    {
+        int npow2 = 64;
+        while (npow2 < ld) npow2 <<= 1;
+        svd_finalize_kernel<<<batch, 256, npow2 * 12, st>>>(bX, stride, ld, d_mv, d_nbv, sing_vals, sv_stride, d_perm, npow2);
+        CK(cudaGetLastError());
+        dim3 grid(lmax, batch);
+        svd_gather_kernel<<<grid, 128, 0, st>>>(bX, bV, stride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bRs, bLt, status);
+        CK(cudaGetLastError());
+    }
+    // ---- reduced operator ----
+    GemmParams gp;
+    gp.sig = (const cplx*)signals; gp.sig_off = d_soff;
+    // T1 = U^p * Rs
+    gp.A = nullptr; gp.strideA = 0; gp.lda = 0;
+    gp.B = bRs; gp.strideB = stride; gp.ldb = ld;
+    gp.C = bT1; gp.strideC = stride; gp.ldc = ld;
+    gp.Mv = d_mv; gp.Nv = d_lv; gp.Kv = d_mv; gp.shift = p;
+    CK(zgemm_batched(A_HANKEL, gp, mmax, lmax, mmax, batch, st));
+    // Ured = Lt^H * T1
+    cplx* bUred = bH;
+    gp.A = bLt; gp.strideA = stride; gp.lda = ld;
+    gp.B = bT1; gp.strideB = stride; gp.ldb = ld;
+    gp.C = bUred; gp.strideC = stride; gp.ldc = ld;
+    gp.Mv = d_lv; gp.Nv = d_lv; gp.Kv = d_mv; gp.shift = 0;
+    CK(zgemm_batched(A_CONJT, gp, lmax, lmax, mmax, batch, st));
+    if (dbg) CK(cudaMemcpyAsync(mat(5), bUred, sizeof(cplx) * batch * stride, cudaMemcpyDeviceToDevice, st));
+    // ---- eigen-decomposition of Ured ----
+    {
+        size_t sm = (size_t)ld * 16 + 512;
+        CK(cudaFuncSetAttribute(hessenberg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        hessenberg_kernel<<<batch, E_THREADS, sm, st>>>(bH, bZ, stride, ld, d_lv, d_tau);
+        CK(cudaGetLastError());
+        if (dbg) {
+            CK(cudaMemcpyAsync(mat(6), bH, sizeof(cplx) * batch * stride, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(mat(7), bZ, sizeof(cplx) * batch * stride, cudaMemcpyDeviceToDevice, st));
+        }
+        CK(cudaFuncSetAttribute(hqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HQR_SMEM_BYTES));
+        hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs);
+        CK(cudaGetLastError());
+        size_t sm2 = (size_t)ld * 32 + 512;
+        CK(cudaFuncSetAttribute(trevc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        trevc_kernel<<<batch, E_THREADS, sm2, st>>>(bH, bXev, stride, ld, d_lv);
+        CK(cudaGetLastError());
+    }
+    // P = Z * Xev
+    gp.A = bZ; gp.strideA = stride; gp.lda = ld;
+    gp.B = bXev; gp.strideB = stride; gp.ldb = ld;
+    gp.C = bP; gp.strideC = stride; gp.ldc = ld;
+    gp.Mv = d_lv; gp.Nv = d_lv; gp.Kv = d_lv;
+    CK(zgemm_batched(A_NORMAL, gp, lmax, lmax, lmax, batch, st));
+    // B = Rs * P
+    gp.A = bRs; gp.B = bP; gp.C = bB;
+    gp.Mv = d_mv; gp.Nv = d_lv; gp.Kv = d_lv;
+    CK(zgemm_batched(A_NORMAL, gp, mmax, lmax, lmax, batch, st));
+    // W = U0 * B
+    gp.A = nullptr; gp.B = bB; gp.C = bW;
+    gp.Mv = d_mv; gp.Nv = d_lv; gp.Kv = d_mv; gp.shift = 0;
+    CK(zgemm_batched(A_HANKEL, gp, mmax, lmax, mmax, batch, st));
+    // ---- amplitudes / line list ----
+    {
+        dim3 grid((lmax + 7) / 8, batch);
+        epilogue_kernel<<<grid, 256, 0, st>>>(bB, bW, bH, stride, ld, d_mv, d_lv, dwell, line_lists, ll_stride,
+                                              (cplx*)mu_out, (cplx*)d_out, mu_stride, n_valid, status);
+        CK(cudaGetLastError());
+    }
+    int h_maxs = 0;
+    if (info) {
+        // max QR sweeps over the batch (diagnostic)
+        int* h = (int*)malloc(sizeof(int) * batch);
+        if (h) {
+            cudaError_t e3 = cudaMemcpyAsync(h, d_hqrs, sizeof(int) * batch, cudaMemcpyDeviceToHost, st);
+            if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(st);
+            if (e3 == cudaSuccess) for (int b = 0; b < batch; ++b) if (h[b] > h_maxs) h_maxs = h[b];
+            free(h);
+            if (e3 != cudaSuccess) return -(int)e3;
+        }
+        info[0] = sweeps_run; info[1] = h_maxs; info[2] = ld; info[3] = nbmax;
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"
