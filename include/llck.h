@@ -43,6 +43,7 @@ extern "C" {
 
 /* flags */
 #define LLCK_FLAG_DEBUG_KEEP 1       /* keep every intermediate in its own workspace matrix (tests only) */
+#define LLCK_FLAG_TIMING 2           /* record CUDA events between stages; durations (us) returned in info[4..12] */
 
 int llck_version(void);
 
@@ -67,7 +68,10 @@ size_t llck_debug_offset(int batch, int ld, int which);
  *   sing_vals  [dev]  float64 [batch][sv_stride]   all m[b] singular values, descending (kbdm.py:68,207)
  *   n_valid    [dev]  int32   [batch]              rows passing filter_samples (A>1e-6 and T2>0, sampling.py:92-95)
  *   status     [dev]  int32   [batch]              LLCK_STATUS_*
- *   info       [host] int32   [4] (optional)       [0]=Jacobi sweeps run, [1]=max QR multishift sweeps, [2..3] reserved
+ *   info       [host] int32   [16] (optional)      [0]=Jacobi sweeps run, [1]=max QR multishift sweeps, [2]=ld, [3]=nbmax,
+ *                                                  [4..12]=stage durations in us when LLCK_FLAG_TIMING (init, jacobi,
+ *                                                  finalize+gather, T1+Ured, hessenberg, hqr, trevc, P+B+W, epilogue),
+ *                                                  [13]=kernel launches issued, [14]=jacobi_step_kernel launches
  */
 int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int32_t* m, const int32_t* l,
                       int32_t p, double q, double dwell, int32_t batch,

@@ -20,6 +20,7 @@ SYMBOLS = (
 )
 
 FLAG_DEBUG_KEEP = 1
+FLAG_TIMING = 2
 
 STATUS_OK = 0
 STATUS_QR_NOCONV = 1

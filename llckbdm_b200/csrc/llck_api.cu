@@ -13,6 +13,7 @@
 #include "svd.cuh"
 #include "eig.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return -(int)e_; } while (0)
 
@@ -145,6 +146,11 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     const WsLayout L = ws_layout(batch, ld, flags);
     if (workspace_bytes < L.total) return LLCK_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool timing = (flags & LLCK_FLAG_TIMING) != 0 && info != nullptr;
+    cudaEvent_t tev[10];
+    int ntev = 0;
+    if (timing) for (int i = 0; i < 10; ++i) CK(cudaEventCreate(&tev[i]));
+#define TICK() do { if (timing) { CK(cudaEventRecord(tev[ntev++], st)); } } while (0)
     unsigned char* ws = (unsigned char*)workspace;
     int* d_mv = (int*)(ws + L.mv);
     int* d_lv = (int*)(ws + L.lv);
@@ -191,16 +197,21 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     CK(cudaMemsetAsync(d_hqrs, 0, sizeof(int) * batch, st));
 
     // ---- SVD of U^{p-1} ----
+    TICK();   // 0
     {
         dim3 grid(256, batch);
         svd_init_kernel<<<grid, 256, 0, st>>>(bX, bV, stride, ld, d_mv, d_nbv, (const cplx*)signals, d_soff, p - 1);
         CK(cudaGetLastError());
     }
+    TICK();   // 1: init done
     CK(cudaFuncSetAttribute(jacobi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, J_SMEM_BYTES));
     JacobiParams jp;
     jp.X = bX; jp.V = bV; jp.stride = stride; jp.ld = ld; jp.mv = d_mv; jp.nbv = d_nbv;
     jp.sweep_off = d_swoff; jp.done = d_done; jp.tol2 = 1e-28;
+    jp.inner_sweeps = 1;
+    if (const char* ev = getenv("LLCK_JACOBI_INNER")) jp.inner_sweeps = atoi(ev);
     int sweeps_run = 0;
+    int launches = 1;   // svd_init
     const int max_sweeps = 30;
     int h_active = batch;
     for (int sweep = 0; sweep < max_sweeps && h_active > 0; ++sweep) {
@@ -209,6 +220,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             dim3 grid(nbmax / 2, batch);
             jacobi_step_kernel<<<grid, 256, J_SMEM_BYTES, st>>>(jp);
         }
+        launches += nbmax - 1 + 1;
         CK(cudaGetLastError());
         CK(cudaMemsetAsync(d_nact, 0, sizeof(int), st));
         jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, d_nact, batch, 1e-14);
@@ -216,6 +228,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         CK(cudaStreamSynchronize(st));
         ++sweeps_run;
     }
+    TICK();   // 2: jacobi done
     if (h_active > 0) {
         mark_unconverged_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_done, status, batch);
         CK(cudaGetLastError());
@@ -229,6 +242,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         svd_gather_kernel<<<grid, 128, 0, st>>>(bX, bV, stride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bRs, bLt, status);
         CK(cudaGetLastError());
     }
+    TICK();   // 3: finalize+gather done
     // ---- reduced operator ----
     GemmParams gp;
     gp.sig = (const cplx*)signals; gp.sig_off = d_soff;
@@ -246,6 +260,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     gp.Mv = d_lv; gp.Nv = d_lv; gp.Kv = d_mv; gp.shift = 0;
     CK(zgemm_batched(A_CONJT, gp, lmax, lmax, mmax, batch, st));
     if (dbg) CK(cudaMemcpyAsync(mat(5), bUred, sizeof(cplx) * batch * stride, cudaMemcpyDeviceToDevice, st));
+    TICK();   // 4: T1 + Ured done
     // ---- eigen-decomposition of Ured ----
     {
         size_t sm = (size_t)ld * 16 + 512;
@@ -256,14 +271,17 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             CK(cudaMemcpyAsync(mat(6), bH, sizeof(cplx) * batch * stride, cudaMemcpyDeviceToDevice, st));
             CK(cudaMemcpyAsync(mat(7), bZ, sizeof(cplx) * batch * stride, cudaMemcpyDeviceToDevice, st));
         }
+        TICK();   // 5: hessenberg done
         CK(cudaFuncSetAttribute(hqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HQR_SMEM_BYTES));
         hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs);
         CK(cudaGetLastError());
+        TICK();   // 6: hqr done
         size_t sm2 = (size_t)ld * 32 + 512;
         CK(cudaFuncSetAttribute(trevc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         trevc_kernel<<<batch, E_THREADS, sm2, st>>>(bH, bXev, stride, ld, d_lv);
         CK(cudaGetLastError());
     }
+    TICK();   // 7: trevc done
     // P = Z * Xev
     gp.A = bZ; gp.strideA = stride; gp.lda = ld;
     gp.B = bXev; gp.strideB = stride; gp.ldb = ld;
@@ -278,6 +296,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     gp.A = nullptr; gp.B = bB; gp.C = bW;
     gp.Mv = d_mv; gp.Nv = d_lv; gp.Kv = d_mv; gp.shift = 0;
     CK(zgemm_batched(A_HANKEL, gp, mmax, lmax, mmax, batch, st));
+    TICK();   // 8: back-transform GEMMs done
     // ---- amplitudes / line list ----
     {
         dim3 grid((lmax + 7) / 8, batch);
@@ -285,6 +304,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
                                               (cplx*)mu_out, (cplx*)d_out, mu_stride, n_valid, status);
         CK(cudaGetLastError());
     }
+    TICK();   // 9: epilogue done
     int h_maxs = 0;
     if (info) {
         // max QR sweeps over the batch (diagnostic)
@@ -297,8 +317,20 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             if (e3 != cudaSuccess) return -(int)e3;
         }
         info[0] = sweeps_run; info[1] = h_maxs; info[2] = ld; info[3] = nbmax;
+        info[13] = launches + 2 /*finalize, gather*/ + 5 /*gemms*/ + 3 /*hessenberg, hqr, trevc*/ + 1 /*epilogue*/;
+        info[14] = sweeps_run * (nbmax - 1);   // jacobi_step_kernel launches
     }
     CK(cudaStreamSynchronize(st));
+    if (timing) {
+        // info[4..12]: stage durations in microseconds: init, jacobi, finalize+gather, T1+Ured, hessenberg, hqr, trevc, P+B+W, epilogue
+        for (int i = 0; i + 1 < ntev; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, tev[i], tev[i + 1]));
+            info[4 + i] = (int32_t)(ms * 1000.0f);
+        }
+        for (int i = 0; i < 10; ++i) cudaEventDestroy(tev[i]);
+    }
+#undef TICK
     return 0;
 }
 

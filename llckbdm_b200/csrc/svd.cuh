@@ -28,6 +28,7 @@ struct JacobiParams {
     unsigned long long* sweep_off;   // per member: max scaled off-diagonal^2 seen this sweep (double bits)
     const int* done;      // per member: converged flag
     double tol2;          // skip a pair when off^2 < tol2
+    int inner_sweeps;     // cap on the two-sided Jacobi sweeps of the 64x64 Gram eigen-solve
 };
 
 // ---- init: X = Hankel(U^{shift}), V = I -----------------------------------------------------------
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256, 1) jacobi_step_kernel(JacobiParams p) {
     if (tid < 64) G[tid + J_LDJ * tid].y = 0.0;
     __syncthreads();
     const double tol_in2 = 4e-30;   // (2e-15)^2
-    for (int sweep = 0; sweep < 24; ++sweep) {
+    for (int sweep = 0; sweep < p.inner_sweeps; ++sweep) {
         if (tid == 0) flags[0] = 0;
         for (int step = 0; step < 63; ++step) {
             __syncthreads();

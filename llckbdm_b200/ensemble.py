@@ -91,7 +91,7 @@ def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=
     sv = torch.empty((batch, mmax), dtype=torch.float64, device=dev)
     n_valid = torch.empty(batch, dtype=torch.int32, device=dev)
     status = torch.empty(batch, dtype=torch.int32, device=dev)
-    info = (ctypes.c_int32 * 4)()
+    info = (ctypes.c_int32 * 16)()
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     rc = lib.llck_kbdm_batched(
         signals_dev.data_ptr(), off_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),

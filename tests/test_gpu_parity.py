@@ -1,0 +1,259 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the public API and the C ABI,
+against the CPU oracle on the same seeded inputs, against the golden vectors of the real reference, the
+reference's own acceptance tests, and -- at full size -- size-independent properties.
+
+Tolerances: per member, rows matched by nearest pole; |dmu|/|mu| <= 1e-8 for ALL rows on
+noisy inputs; |dD|/|D| <= 1e-8 for rows with |D| > 1e-3 max|D|; singular values rel 1e-8 (abs 1e-12)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DWELL = 5e-4
+TOL = 1e-8
+
+
+def _D(ll):
+    return ll[:, 0] * np.exp(1j * ll[:, 3])
+
+
+def _compare_ll(ll_gpu, ll_ref):
+    from oracle.kbdm_oracle import compare_members, mu_from_line_list
+    return compare_members(mu_from_line_list(ll_gpu, DWELL), _D(ll_gpu), mu_from_line_list(ll_ref, DWELL), _D(ll_ref))
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from llckbdm_b200 import _native
+    _native.load()        # fails loudly if the in-tree extension is missing
+    return torch
+
+
+@pytest.mark.parametrize("name", ["noisy_m16", "noisy_m64", "noisy_m128", "noisy_m200_l30", "noisy_m96_p2", "noisy_m80_q",
+                                  "noisy_m100_l40_p2_q", "noisy_m256"])
+def test_kbdm_matches_reference_golden(cuda, golden_dir, name):
+    from llckbdm_b200.kbdm import kbdm
+    g = np.load(os.path.join(golden_dir, f"kbdm_{name}.npz"))
+    l = None if int(g["l"]) < 0 else int(g["l"])
+    ll, info = kbdm(g["data"], float(g["dwell"]), m=int(g["m"]), p=int(g["p"]), l=l, q=float(g["q"]))
+    assert ll.shape == g["line_list"].shape and ll.dtype == np.float64
+    dmu, dD = _compare_ll(ll, g["line_list"])
+    assert dmu < TOL and dD < TOL, (dmu, dD)
+    assert info.singular_values.shape == (int(g["m"]),)
+    assert np.allclose(info.singular_values, g["singular_values"], rtol=1e-8, atol=1e-12)
+    assert info.m == int(g["m"]) and info.p == int(g["p"]) and info.q == float(g["q"])
+
+
+def test_known_answer_16_components_reference_test_kbdm_svd(cuda):
+    """Same assertions as reference llckbdm/_tests/test_kbdm.py:8-42, GPU backend."""
+    from llckbdm_b200.kbdm import kbdm
+    from oracle.kbdm_oracle import BRAIN_SIM_PARAMS, brain_sim
+    ll, info = kbdm(brain_sim(2048, 0.0, 0), DWELL, m=300)
+    assert ll.shape == (300, 4) and info.m == 300 and info.l == 300 and info.p == 1 and info.q == 0
+    est = ll[ll[:, 0] > 1e-4]
+    est = est[np.argsort(est[:, 2])]
+    assert len(est) == 16
+    assert np.allclose(est[:, 0], BRAIN_SIM_PARAMS[:, 0], rtol=1e-6)
+    assert np.allclose(est[:, 1], BRAIN_SIM_PARAMS[:, 1], rtol=1e-3)
+    assert np.allclose(est[:, 2], BRAIN_SIM_PARAMS[:, 2], atol=0.3)
+    assert np.allclose(est[:, 3], 0.0, atol=1e-10)
+
+
+def test_m_l_defaults_and_validation_on_gpu_api(cuda, caplog):
+    """Reference _tests/test_kbdm.py:62-122."""
+    from llckbdm_b200.kbdm import kbdm
+    from oracle.kbdm_oracle import brain_sim
+    c = brain_sim(2048, 0.0, 0)
+    with pytest.raises(ValueError, match="l or m must be specified"):
+        kbdm(data=c, dwell=DWELL)
+    with pytest.raises(ValueError, match="l can't be greater than m"):
+        kbdm(data=c, dwell=DWELL, l=30, m=20)
+    with pytest.raises(ValueError, match=r"m or l can't be greater than \(n \+ 1 - p\)/2."):
+        kbdm(data=c, dwell=DWELL, m=1025)
+    ll, info = kbdm(data=c, dwell=DWELL, l=30)
+    assert ll.shape == (30, 4) and info.l == 30 and info.m == 30
+    caplog.set_level('DEBUG')
+    ll, info = kbdm(c, DWELL, m=10, q=1e-3)
+    assert 'Using Tikhonov Regularization' in caplog.text
+    assert ll.shape == (10, 4) and info.q == pytest.approx(1e-3)
+
+
+def test_sample_kbdm_batched_equals_oracle_members(cuda):
+    """One batched launch over ragged sizes (incl. m not a multiple of 32, l < m) == per-member oracle."""
+    from llckbdm_b200.sampling import sample_kbdm
+    from oracle.kbdm_oracle import brain_sim, kbdm_oracle
+    c = brain_sim(2048, 1e-3, 5)
+    m_range = [33, 100, 64, 257, 150, 7, 96]
+    lls, infos = sample_kbdm(c, DWELL, m_range, p=1, l=None, q=0, filter_invalid_features=False)
+    assert len(lls) == len(m_range) == len(infos)
+    for m, ll, info in zip(m_range, lls, infos):
+        ll_o, info_o = kbdm_oracle(c, DWELL, m=m)
+        assert ll.shape == (m, 4) and info.m == m
+        dmu, dD = _compare_ll(ll, ll_o)
+        assert dmu < TOL and dD < TOL, (m, dmu, dD)
+        assert np.allclose(info.singular_values, info_o.singular_values, rtol=1e-8, atol=1e-12)
+
+
+def test_sample_kbdm_reference_contract(cuda):
+    """Reference _tests/test_sampling.py:19-62: equality with direct kbdm, filter leaves the 16 true lines."""
+    from llckbdm_b200.kbdm import kbdm
+    from llckbdm_b200.sampling import filter_samples, sample_kbdm
+    from oracle.kbdm_oracle import BRAIN_SIM_PARAMS, brain_sim
+    c = brain_sim(2048, 0.0, 0)
+    lls, infos = sample_kbdm(c, DWELL, range(100, 103), p=1, l=None, q=0, filter_invalid_features=False)
+    assert len(lls) == 3
+    ll0, info0 = kbdm(c, DWELL, m=100, p=1, l=None)
+    big = ll0[:, 0] > 1e-4
+    assert big.sum() == 16
+    a = lls[0][lls[0][:, 0] > 1e-4]
+    assert np.allclose(np.sort(a[:, 2]), np.sort(ll0[big, 2]), rtol=1e-9)
+    assert infos[0].m == info0.m and infos[0].l == info0.l
+    assert np.allclose(infos[0].singular_values[:16], info0.singular_values[:16], rtol=1e-9)
+    f = filter_samples(kbdm(c, DWELL, m=150)[0])
+    assert len(f) == 16
+    f = f[np.argsort(f[:, 0])]
+    truth = BRAIN_SIM_PARAMS[np.argsort(BRAIN_SIM_PARAMS[:, 0])]
+    assert np.allclose(f[0], truth[0], atol=0.01) and np.allclose(f[-1], truth[-1], atol=0.01)
+
+
+def test_min_rmse_kbdm_reference_test(cuda):
+    """Reference _tests/test_min_rmse_kbdm.py:6-23: min_index == 2, rmse ~ 0."""
+    from llckbdm_b200.min_rmse_kbdm import min_rmse_kbdm
+    from oracle.kbdm_oracle import brain_sim
+    r = min_rmse_kbdm(data=brain_sim(2048, 0.0, 0), dwell=DWELL, m_range=[30, 31, 180, 32, 33, 34], l=30)
+    assert len(r.samples) == 6
+    assert r.min_rmse == pytest.approx(0, abs=1e-6)
+    assert r.min_index == 2
+
+
+def test_llc_kbdm_reference_test(cuda):
+    """Reference _tests/test_llckbdm.py:37-57: 16 lines after clustering, residual std < 1e-3."""
+    from llckbdm_b200.llckbdm import llc_kbdm
+    from llckbdm_b200.sig_gen import multi_fid
+    from oracle.kbdm_oracle import brain_sim
+    c = brain_sim(2048, 0.0, 0)
+    res = llc_kbdm(c, DWELL, m_range=range(250, 260), l=30)
+    ll = res.line_list[res.line_list[:, 0] > 1e-3]
+    assert len(ll) == 16
+    t = np.linspace(0, DWELL * 2048, 2048, endpoint=False)
+    resid = c - multi_fid(t, ll)
+    assert np.std(resid.real) < 1e-3 and np.std(resid.imag) < 1e-3
+    with pytest.raises(ValueError, match="size of 'm_range' must be greater than 2."):
+        llc_kbdm(c, DWELL, m_range=[100])
+
+
+def test_llc_kbdm_cluster_parity_noisy(cuda):
+    """Clustered estimates from GPU line lists == clustered estimates from oracle line lists (same CPU clusterer),
+    rel 1e-6, identical cluster count."""
+    from llckbdm_b200 import llckbdm as L
+    from llckbdm_b200.sampling import filter_samples, sample_kbdm
+    from oracle.kbdm_oracle import brain_sim, sample_kbdm_oracle
+    c = brain_sim(2048, 1e-3, 11)
+    m_range = list(range(120, 128))
+    gpu, _ = sample_kbdm(c, DWELL, m_range, p=1, l=None)
+    ref, _ = sample_kbdm_oracle(c, DWELL, m_range, p=1, l=None)
+    assert [len(a) for a in gpu] == [len(a) for a in ref]
+    out = []
+    for lls in (gpu, ref):
+        s = np.concatenate([a[np.lexsort((a[:, 0], a[:, 2]))] for a in lls])     # canonical row order
+        s = filter_samples(s)
+        r = L._cluster_line_lists(s, L._transform_line_lists(s, DWELL), min_samples=4)
+        out.append((r.num_clusters, np.asarray(r.labels), np.asarray(r.summarized_line_list)))
+    assert out[0][0] == out[1][0] and out[0][0] > 0
+    assert np.array_equal(out[0][1], out[1][1])
+    a, b = out[0][2], out[1][2]
+    assert np.allclose(a[:, [0, 2]], b[:, [0, 2]], rtol=1e-6, atol=1e-9)
+    assert np.allclose(a[:, 1], b[:, 1], rtol=1e-6)
+
+
+def test_singular_member_raises_linalgerror(cuda):
+    """Exact zero singular value among the kept ones -> LinAlgError (np.linalg.inv behaviour at kbdm.py:186)."""
+    from llckbdm_b200.kbdm import kbdm
+    with pytest.raises(np.linalg.LinAlgError):
+        kbdm(np.zeros(64, dtype=complex), DWELL, m=8)
+
+
+def test_real_input_is_accepted(cuda):
+    from llckbdm_b200.kbdm import kbdm
+    from oracle.kbdm_oracle import brain_sim, kbdm_oracle
+    c = brain_sim(256, 1e-3, 2).real.copy()
+    ll, info = kbdm(c, DWELL, m=40)
+    ll_o, _ = kbdm_oracle(c.astype(complex), DWELL, m=40)
+    dmu, dD = _compare_ll(ll, ll_o)
+    assert dmu < TOL and dD < TOL
+
+
+def test_zgemm_stage_entry_hankel_and_conjt(cuda):
+    """The production DMMA GEMM kernel through llck_zgemm: implicit Hankel operand, conj-transpose and plain."""
+    torch = cuda
+    from llckbdm_b200 import _native
+    lib = _native.load()
+    rng = np.random.default_rng(0)
+    M, N, K = 150, 70, 131
+    sig = rng.standard_normal(M + K + 5) + 1j * rng.standard_normal(M + K + 5)
+    B = rng.standard_normal((K, N)) + 1j * rng.standard_normal((K, N))
+    A = rng.standard_normal((M, K)) + 1j * rng.standard_normal((M, K))
+    dev = torch.device("cuda:0")
+
+    def to_dev(x):   # column-major device copy
+        return torch.from_numpy(np.asfortranarray(x).T.copy().view(np.float64)).to(dev)
+
+    def run(amode, Ad, lda, shift=0):
+        Cd = torch.zeros((N, M, 2), dtype=torch.float64, device=dev)
+        rc = lib.llck_zgemm(amode, Ad.data_ptr() if Ad is not None else None, lda, Bd.data_ptr(), K, Cd.data_ptr(), M,
+                            M, N, K, sigd.data_ptr(), shift, None)
+        assert rc == 0
+        return Cd.cpu().numpy().view(np.complex128)[..., 0].T
+
+    Bd, sigd = to_dev(B), torch.from_numpy(sig.view(np.float64)).to(dev)
+    H = sig[np.arange(M)[:, None] + np.arange(K)[None, :] + 3]
+    assert np.abs(run(2, None, 0, shift=3) - H @ B).max() < 1e-11
+    assert np.abs(run(0, to_dev(A), M) - A @ B).max() < 1e-11
+    At = rng.standard_normal((K, M)) + 1j * rng.standard_normal((K, M))
+    assert np.abs(run(1, to_dev(At), K) - At.conj().T @ B).max() < 1e-11
+
+
+def test_full_size_m1024_properties(cuda):
+    """BASELINE size (N=2048, m=l=1024): size-independent properties instead of the (slow) oracle eig:
+    singular values vs LAPACK, generalized-eigen residual of every pole, amplitude identity, signal reconstruction."""
+    from llckbdm_b200.ensemble import solve_ensemble
+    from oracle.kbdm_oracle import brain_sim, hankel_matrices
+    c = brain_sim(2048, 1e-3, 0)
+    m = 1024
+    res = solve_ensemble(c, [m], [m], 1, 0.0, DWELL)
+    assert res.status[0] == 0
+    U0, _, U1 = hankel_matrices(c, m, 1)
+    s_ref = np.linalg.svd(U0, compute_uv=False)
+    assert np.allclose(res.sing_vals[0], s_ref, rtol=1e-8, atol=1e-12)
+    mu, D = res.mu[0], res.D[0]
+    # every pole is a generalized eigenvalue of (U1, U0): sigma_min(U1 - mu U0) ~ 0, checked on a sample of poles
+    smax = s_ref[0]
+    for k in np.linspace(0, m - 1, 6).astype(int):
+        smin = np.linalg.svd(U1 - mu[k] * U0, compute_uv=False)[-1]
+        assert smin < 1e-9 * smax
+    # sum_k D_k mu_k^n reproduces the signal (harmonic inversion is exact for l = m); checked on the first 64 points
+    n = np.arange(64)
+    recon = (D[None, :] * mu[None, :] ** n[:, None]).sum(axis=1)
+    assert np.abs(recon - c[:64]).max() < 1e-7 * np.abs(c).max()
+    ll = res.line_lists[0]
+    assert np.allclose(ll[:, 0], np.abs(D)) and np.allclose(ll[:, 3], np.angle(D))
+
+
+def test_c2_ensemble_shape_subset_parity(cuda):
+    """A slice of config C2 (m in [700,1024], ragged batch) against the oracle on the two smallest members."""
+    from llckbdm_b200.ensemble import solve_ensemble
+    from oracle.kbdm_oracle import brain_sim, compare_members, kbdm_oracle
+    c = brain_sim(2048, 1e-3, 0)
+    ms = [700, 703, 1024, 857]
+    res = solve_ensemble(c, ms, ms, 1, 0.0, DWELL)
+    assert (res.status == 0).all()
+    for k in (0, 1):
+        _, info_o, mu_o, D_o = kbdm_oracle(c, DWELL, m=ms[k], return_mu=True)
+        dmu, dD = compare_members(res.mu[k, :ms[k]], res.D[k, :ms[k]], mu_o, D_o)
+        assert dmu < TOL and dD < TOL, (ms[k], dmu, dD)
+        assert np.allclose(res.sing_vals[k, :ms[k]], info_o.singular_values, rtol=1e-8, atol=1e-12)
