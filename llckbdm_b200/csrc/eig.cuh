@@ -115,6 +115,208 @@ __global__ void __launch_bounds__(E_THREADS, 1) hessenberg_kernel(cplx* H, cplx*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Blocked (compact-WY) Hessenberg reduction: panel kernel.
+// For the panel of HB_NB columns starting at k0 it generates reflectors v_j (P_j = I - tau_j v_j v_j^H), the upper
+// triangular T (Q = P_0..P_{nb-1} = I - V T V^H) and Y = A V T, reading the trailing matrix ONCE per column (the gemv
+// A[:, c+1:] v) and never writing it; the trailing updates  A[:, e:] -= Y V[e:,:]^H  and  A[k0+1:, e:] -= V (V T)^H A
+// are done afterwards by the batched DMMA GEMM.  Panel columns are finished in-panel:
+//   b = A[:,c] - Y V[c,:]^H ;  b -= V T^H (V^H b).
+// Outputs (per member, leading dimension ld, HB_NB columns, zero-filled where unused):
+//   Vp explicit V (unit diagonal, zeros above), Yp, VTp = V*T, Tws[panel] = T; v is also kept below the subdiagonal of H.
+// dynamic smem: (2*ld + HB_NB*HB_NB + 4*HB_NB) * 16 + 512
+// ---------------------------------------------------------------------------------------------
+#define HB_NB 32
+__global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long long stride, int ld, const int* lv, int k0,
+                                                                  cplx* Vp, cplx* Yp, cplx* VTp, long long pstride,
+                                                                  cplx* Tws, long long tstride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* bvec = reinterpret_cast<cplx*>(smem_raw);       // ld
+    cplx* vvec = bvec + ld;                                // ld
+    cplx* Tsm = vvec + ld;                                 // HB_NB x HB_NB (col-major, ld HB_NB)
+    cplx* w1 = Tsm + HB_NB * HB_NB;                        // HB_NB
+    cplx* w2 = w1 + HB_NB;                                 // HB_NB
+    cplx* zv = w2 + HB_NB;                                 // HB_NB
+    cplx* vrow = zv + HB_NB;                               // HB_NB : conj(V[c, :j])
+    double* red = reinterpret_cast<double*>(vrow + HB_NB);
+    const int b = blockIdx.x, n = lv[b];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (k0 + 2 >= n) return;                               // nothing left to reduce for this member
+    cplx* Hb = H + (long long)b * stride;
+    cplx* Vb = Vp + (long long)b * pstride;
+    cplx* Yb = Yp + (long long)b * pstride;
+    cplx* VTb = VTp + (long long)b * pstride;
+    cplx* Tb = Tws + (long long)b * tstride + (long long)(k0 / HB_NB) * HB_NB * HB_NB;
+
+    for (int idx = tid; idx < HB_NB * HB_NB; idx += E_THREADS) Tsm[idx] = mkc(0.0, 0.0);
+    for (int idx = tid; idx < ld * HB_NB; idx += E_THREADS) { Vb[idx] = mkc(0.0, 0.0); Yb[idx] = mkc(0.0, 0.0); }
+    __syncthreads();
+
+    for (int j = 0; j < HB_NB; ++j) {
+        const int c = k0 + j;
+        if (c >= n) break;
+        cplx* colc = Hb + (long long)ld * c;
+        // ---- b = A[:,c] - Y[:, :j] conj(V[c, :j]) ----
+        if (tid < j) vrow[tid] = cconj(Vb[c + (long long)ld * tid]);
+        __syncthreads();
+        for (int i = tid; i < n; i += E_THREADS) {
+            cplx acc = colc[i];
+            for (int jj = 0; jj < j; ++jj) acc = csub(acc, cmul(Yb[i + (long long)ld * jj], vrow[jj]));
+            bvec[i] = acc;
+        }
+        __syncthreads();
+        // ---- b -= V (T^H (V^H b)) ----
+        if (j > 0) {
+            for (int jj = warp; jj < j; jj += E_NWARPS) {
+                const cplx* vc = Vb + (long long)ld * jj;
+                cplx d = mkc(0.0, 0.0);
+                for (int i = k0 + jj + 1 + lane; i < n; i += 32) d = cfmac(vc[i], bvec[i], d);
+                d = warp_sum(d);
+                if (lane == 0) w1[jj] = d;
+            }
+            __syncthreads();
+            if (tid < j) {        // w2 = T^H w1 : w2[r] = sum_{q<=r} conj(T[q,r]) w1[q]
+                cplx a = mkc(0.0, 0.0);
+                for (int q = 0; q <= tid; ++q) a = cfmac(Tsm[q + HB_NB * tid], w1[q], a);
+                w2[tid] = a;
+            }
+            __syncthreads();
+            for (int i = k0 + 1 + tid; i < n; i += E_THREADS) {
+                cplx acc = bvec[i];
+                for (int jj = 0; jj < j; ++jj) acc = csub(acc, cmul(Vb[i + (long long)ld * jj], w2[jj]));
+                bvec[i] = acc;
+            }
+            __syncthreads();
+        }
+        if (c + 2 >= n) {
+            // last two columns of the matrix: no reflector, just store the updated column
+            for (int i = tid; i < n; i += E_THREADS) colc[i] = bvec[i];
+            __syncthreads();
+            continue;
+        }
+        // ---- reflector from b[c+1:] ----
+        double part = 0.0;
+        for (int i = c + 2 + tid; i < n; i += E_THREADS) part += cabs2(bvec[i]);
+        const double xnorm2 = block_sum(part, red);
+        const cplx alpha = bvec[c + 1];
+        cplx tau = mkc(0.0, 0.0);
+        double beta = alpha.x;
+        cplx scale = mkc(0.0, 0.0);
+        const bool trivial = (xnorm2 == 0.0 && alpha.y == 0.0);
+        if (!trivial) {
+            beta = -copysign(sqrt(cabs2(alpha) + xnorm2), alpha.x);
+            tau = mkc((beta - alpha.x) / beta, -alpha.y / beta);
+            scale = cdiv(mkc(1.0, 0.0), mkc(alpha.x - beta, alpha.y));
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += E_THREADS) {
+            cplx vv = mkc(0.0, 0.0), hv = bvec[i];
+            if (i == c + 1) { vv = mkc(1.0, 0.0); hv = trivial ? alpha : mkc(beta, 0.0); }
+            else if (i > c + 1) { vv = trivial ? mkc(0.0, 0.0) : cmul(bvec[i], scale); hv = vv; }
+            vvec[i] = vv;
+            Vb[i + (long long)ld * j] = vv;
+            colc[i] = hv;                       // Hessenberg column above/at the subdiagonal, v stored below it
+        }
+        __syncthreads();
+        // ---- z = V[:, :j]^H v ;  T[:j, j] = -tau T[:j,:j] z ; T[j,j] = tau ----
+        for (int jj = warp; jj < j; jj += E_NWARPS) {
+            const cplx* vc = Vb + (long long)ld * jj;
+            cplx d = mkc(0.0, 0.0);
+            for (int i = c + 1 + lane; i < n; i += 32) d = cfmac(vc[i], vvec[i], d);
+            d = warp_sum(d);
+            if (lane == 0) zv[jj] = d;
+        }
+        __syncthreads();
+        if (tid < j) {
+            cplx a = mkc(0.0, 0.0);
+            for (int q = tid; q < j; ++q) a = cfma(Tsm[tid + HB_NB * q], zv[q], a);
+            Tsm[tid + HB_NB * j] = cneg(cmul(tau, a));
+        }
+        if (tid == 0) Tsm[j + HB_NB * j] = tau;
+        // ---- y = tau (A[:, c+1:] v[c+1:] - Y[:, :j] z)  (the one pass over the trailing matrix) ----
+        for (int i = tid; i < n; i += E_THREADS) {
+            const cplx* row = Hb + i + (long long)ld * (c + 1);
+            const cplx* vv = vvec + (c + 1);
+            const int len = n - c - 1;
+            cplx y0 = mkc(0.0, 0.0), y1 = mkc(0.0, 0.0), y2 = mkc(0.0, 0.0), y3 = mkc(0.0, 0.0);
+            int q = 0;
+            for (; q + 3 < len; q += 4) {
+                cplx a0 = row[(long long)ld * q], a1 = row[(long long)ld * (q + 1)], a2 = row[(long long)ld * (q + 2)], a3 = row[(long long)ld * (q + 3)];
+                y0 = cfma(a0, vv[q], y0); y1 = cfma(a1, vv[q + 1], y1); y2 = cfma(a2, vv[q + 2], y2); y3 = cfma(a3, vv[q + 3], y3);
+            }
+            for (; q < len; ++q) y0 = cfma(row[(long long)ld * q], vv[q], y0);
+            cplx y = cadd(cadd(y0, y1), cadd(y2, y3));
+            for (int jj = 0; jj < j; ++jj) y = csub(y, cmul(Yb[i + (long long)ld * jj], zv[jj]));
+            Yb[i + (long long)ld * j] = cmul(tau, y);
+        }
+        __syncthreads();
+    }
+    // ---- VT = V * T (rows k0+1..n-1), T to global ----
+    for (int idx = tid; idx < HB_NB * HB_NB; idx += E_THREADS) Tb[idx] = Tsm[idx];
+    __syncthreads();
+    for (int i = tid; i < ld; i += E_THREADS) {
+        const bool live = (i > k0 && i < n);
+        for (int jj = 0; jj < HB_NB; ++jj) {
+            cplx a = mkc(0.0, 0.0);
+            if (live)
+                for (int q = 0; q <= jj; ++q) a = cfma(Vb[i + (long long)ld * q], Tsm[q + HB_NB * jj], a);
+            VTb[i + (long long)ld * jj] = a;
+        }
+    }
+}
+
+// Q formation, one panel (processed in reverse order): rebuilds the explicit V of the panel from the reflectors stored
+// below the subdiagonal of H and writes VTp = V * T^H, so that  Q[k0+1:, k0+1:] -= V ((V T^H)^H Q[k0+1:, k0+1:]).
+__global__ void __launch_bounds__(E_THREADS, 1) hess_qpanel_kernel(const cplx* H, long long stride, int ld, const int* lv, int k0,
+                                                                   cplx* Vp, cplx* VTp, long long pstride, const cplx* Tws, long long tstride) {
+    __shared__ cplx Tsm[HB_NB * HB_NB];
+    const int b = blockIdx.x, n = lv[b];
+    const int tid = threadIdx.x;
+    if (k0 + 2 >= n) return;
+    const cplx* Hb = H + (long long)b * stride;
+    cplx* Vb = Vp + (long long)b * pstride;
+    cplx* VTb = VTp + (long long)b * pstride;
+    const cplx* Tb = Tws + (long long)b * tstride + (long long)(k0 / HB_NB) * HB_NB * HB_NB;
+    for (int idx = tid; idx < HB_NB * HB_NB; idx += E_THREADS) Tsm[idx] = Tb[idx];
+    __syncthreads();
+    for (int i = tid; i < ld; i += E_THREADS) {
+        for (int q = 0; q < HB_NB; ++q) {
+            const int c = k0 + q;
+            cplx vv = mkc(0.0, 0.0);
+            if (c + 2 < n && i < n) {
+                if (i == c + 1) vv = mkc(1.0, 0.0);
+                else if (i > c + 1) vv = Hb[i + (long long)ld * c];
+            }
+            Vb[i + (long long)ld * q] = vv;
+        }
+        for (int jj = 0; jj < HB_NB; ++jj) {          // (V T^H)[i,jj] = sum_{q>=jj} V[i,q] conj(T[jj,q])
+            cplx a = mkc(0.0, 0.0);
+            for (int q = jj; q < HB_NB; ++q) a = cfma(Vb[i + (long long)ld * q], cconj(Tsm[jj + HB_NB * q]), a);
+            VTb[i + (long long)ld * jj] = a;
+        }
+    }
+}
+
+__global__ void set_identity_kernel(cplx* Q, long long stride, int ld, const int* lv) {
+    const int b = blockIdx.y, n = lv[b];
+    cplx* Qb = Q + (long long)b * stride;
+    const long long total = (long long)ld * n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(idx % ld), j = (int)(idx / ld);
+        Qb[idx] = mkc(i == j ? 1.0 : 0.0, 0.0);
+    }
+}
+
+__global__ void clear_below_subdiag_kernel(cplx* H, long long stride, int ld, const int* lv) {
+    const int b = blockIdx.y, n = lv[b];
+    cplx* Hb = H + (long long)b * stride;
+    const long long total = (long long)ld * n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(idx % ld), j = (int)(idx / ld);
+        if (i > j + 1 && i < n) Hb[idx] = mkc(0.0, 0.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // small dense Hessenberg QR in shared memory, executed by ONE warp (all lanes run the same control flow)
 // Hs: n x n upper Hessenberg (ld ldh) -> upper triangular; W (optional, wrows x n, ld ldw) <- W * (rotations)
 // returns number of QR sweeps, or -1 on non-convergence

@@ -18,10 +18,19 @@ struct GemmParams {
     const cplx* A; long long strideA; int lda;       // unused for A_HANKEL
     const cplx* B; long long strideB; int ldb;
     cplx* C;       long long strideC; int ldc;
-    const int* Mv; const int* Nv; const int* Kv;     // per-member dims (device arrays, length batch)
+    const int* Mv; const int* Nv; const int* Kv;     // per-member dims (device arrays, length batch; may be null)
+    int Mc, Nc, Kc;                                  // constants added to the per-member dims (dims = v[b] + c)
+    int accum;                                       // 0: C = A*B ; 1: C -= A*B
     // Hankel source
     const cplx* sig; const long long* sig_off; int shift;
 };
+
+static inline GemmParams gemm_params_zero() {
+    GemmParams p;
+    p.A = nullptr; p.strideA = 0; p.lda = 0; p.B = nullptr; p.strideB = 0; p.ldb = 0; p.C = nullptr; p.strideC = 0; p.ldc = 0;
+    p.Mv = p.Nv = p.Kv = nullptr; p.Mc = p.Nc = p.Kc = 0; p.accum = 0; p.sig = nullptr; p.sig_off = nullptr; p.shift = 0;
+    return p;
+}
 
 #define G_BM 64
 #define G_BN 64
@@ -33,14 +42,15 @@ struct GemmParams {
 #define G_B_ELEMS 1280
 #define G_SIG_MAX 4352  // max Hankel slice (complex) kept in smem: supports m up to 2048+
 
-template <int AMODE>
+// BCONJT: the B operand is stored N x K column-major and used as conj(B)^T (C -= Y * V^H)
+template <int AMODE, bool BCONJT>
 __global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* smem = reinterpret_cast<cplx*>(smem_raw);
     const int b = blockIdx.z;
-    const int M = p.Mv[b], N = p.Nv[b], K = p.Kv[b];
+    const int M = (p.Mv ? p.Mv[b] : 0) + p.Mc, N = (p.Nv ? p.Nv[b] : 0) + p.Nc, K = (p.Kv ? p.Kv[b] : 0) + p.Kc;
     const int row0 = blockIdx.x * G_BM, col0 = blockIdx.y * G_BN;
-    if (row0 >= M || col0 >= N) return;
+    if (row0 >= M || col0 >= N || K <= 0) return;
 
     cplx* As[2];
     cplx* Bs[2];
@@ -94,13 +104,24 @@ __global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
                 cp_async16(&As[buf][k + G_LDA_T * i], src, ok);
             }
         }
+        if (BCONJT) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            int idx = tid + 256 * r;
-            int k = idx & 15, j = idx >> 4;
-            bool ok = (col0 + j < N) && (k0 + k < K);
-            const cplx* src = ok ? (Bg + (k0 + k) + (long long)p.ldb * (col0 + j)) : Bg;
-            cp_async16(&Bs[buf][k + G_LDB * j], src, ok);
+            for (int r = 0; r < 4; ++r) {
+                int idx = tid + 256 * r;
+                int j = idx & 63, k = idx >> 6;
+                bool ok = (col0 + j < N) && (k0 + k < K);
+                const cplx* src = ok ? (Bg + (col0 + j) + (long long)p.ldb * (k0 + k)) : Bg;
+                cp_async16(&Bs[buf][k + G_LDB * j], src, ok);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int idx = tid + 256 * r;
+                int k = idx & 15, j = idx >> 4;
+                bool ok = (col0 + j < N) && (k0 + k < K);
+                const cplx* src = ok ? (Bg + (k0 + k) + (long long)p.ldb * (col0 + j)) : Bg;
+                cp_async16(&Bs[buf][k + G_LDB * j], src, ok);
+            }
         }
         cp_async_commit();
     };
@@ -124,11 +145,11 @@ __global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
         }
         __syncthreads();
         if (AMODE == A_NORMAL) {
-            warp_zmma<2, 4, false, false>(acc, As[buf] + 16 * wr, 1, G_LDA_N, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
+            warp_zmma<2, 4, false, BCONJT>(acc, As[buf] + 16 * wr, 1, G_LDA_N, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
         } else if (AMODE == A_CONJT) {
-            warp_zmma<2, 4, true, false>(acc, As[buf] + G_LDA_T * (16 * wr), G_LDA_T, 1, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
+            warp_zmma<2, 4, true, BCONJT>(acc, As[buf] + G_LDA_T * (16 * wr), G_LDA_T, 1, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
         } else {
-            warp_zmma<2, 4, false, false>(acc, sigs + 16 * wr + kt * G_BK, 1, 1, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
+            warp_zmma<2, 4, false, BCONJT>(acc, sigs + 16 * wr + kt * G_BK, 1, 1, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
         }
         __syncthreads();
     }
@@ -142,8 +163,13 @@ __global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = col0 + 32 * wc + 8 * j + 2 * t;
-            if (c < N) Cg[r + (long long)p.ldc * c] = mkc(acc[i][j][0], acc[i][j][2]);
-            if (c + 1 < N) Cg[r + (long long)p.ldc * (c + 1)] = mkc(acc[i][j][1], acc[i][j][3]);
+            if (p.accum) {
+                if (c < N) { cplx* e = Cg + r + (long long)p.ldc * c; cplx o = *e; *e = mkc(o.x - acc[i][j][0], o.y - acc[i][j][2]); }
+                if (c + 1 < N) { cplx* e = Cg + r + (long long)p.ldc * (c + 1); cplx o = *e; *e = mkc(o.x - acc[i][j][1], o.y - acc[i][j][3]); }
+            } else {
+                if (c < N) Cg[r + (long long)p.ldc * c] = mkc(acc[i][j][0], acc[i][j][2]);
+                if (c + 1 < N) Cg[r + (long long)p.ldc * (c + 1)] = mkc(acc[i][j][1], acc[i][j][3]);
+            }
         }
     }
 }
@@ -154,25 +180,21 @@ static inline size_t zgemm_smem_bytes(int amode, int Kmax) {
 }
 
 // Launch: grid = (ceil(Mmax/64), ceil(Nmax/64), batch)
+template <int AMODE, bool BCONJT>
+static inline cudaError_t zgemm_launch(const GemmParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(zgemm_batched_kernel<AMODE, BCONJT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    zgemm_batched_kernel<AMODE, BCONJT><<<grid, 256, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
 static inline cudaError_t zgemm_batched(int amode, const GemmParams& p, int Mmax, int Nmax, int Kmax, int batch,
-                                        cudaStream_t stream) {
-    if (batch <= 0 || Mmax <= 0 || Nmax <= 0) return cudaSuccess;
+                                        cudaStream_t stream, bool bconjt = false) {
+    if (batch <= 0 || Mmax <= 0 || Nmax <= 0 || Kmax <= 0) return cudaSuccess;
     dim3 grid((Mmax + G_BM - 1) / G_BM, (Nmax + G_BN - 1) / G_BN, batch);
     size_t smem = zgemm_smem_bytes(amode, Kmax);
-    cudaError_t e;
-    if (amode == A_NORMAL) {
-        e = cudaFuncSetAttribute(zgemm_batched_kernel<A_NORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        zgemm_batched_kernel<A_NORMAL><<<grid, 256, smem, stream>>>(p);
-    } else if (amode == A_CONJT) {
-        e = cudaFuncSetAttribute(zgemm_batched_kernel<A_CONJT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        zgemm_batched_kernel<A_CONJT><<<grid, 256, smem, stream>>>(p);
-    } else {
-        if (64 + Kmax + 32 > G_SIG_MAX) return cudaErrorInvalidValue;
-        e = cudaFuncSetAttribute(zgemm_batched_kernel<A_HANKEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        zgemm_batched_kernel<A_HANKEL><<<grid, 256, smem, stream>>>(p);
-    }
-    return cudaGetLastError();
+    if (amode == A_NORMAL) return bconjt ? zgemm_launch<A_NORMAL, true>(p, grid, smem, stream) : zgemm_launch<A_NORMAL, false>(p, grid, smem, stream);
+    if (amode == A_CONJT) return zgemm_launch<A_CONJT, false>(p, grid, smem, stream);
+    if (64 + Kmax + 32 > G_SIG_MAX) return cudaErrorInvalidValue;
+    return zgemm_launch<A_HANKEL, false>(p, grid, smem, stream);
 }

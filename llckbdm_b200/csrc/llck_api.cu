@@ -58,7 +58,7 @@ __global__ void mark_unconverged_kernel(const int* done, int* status, int batch)
 
 // ---- workspace layout -----------------------------------------------------------------------------
 struct WsLayout {
-    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, mats, total;
+    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, mats, total;
     int nmats;
 };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -75,6 +75,12 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
     L.sig_off = o; o = al256(o + sizeof(long long) * batch);
     L.sweep_off = o; o = al256(o + sizeof(unsigned long long) * batch);
     L.tau = o; o = al256(o + sizeof(cplx) * (size_t)batch * ld);
+    const size_t pan = sizeof(cplx) * (size_t)batch * ld * HB_NB;
+    L.vp = o; o = al256(o + pan);
+    L.yp = o; o = al256(o + pan);
+    L.vtp = o; o = al256(o + pan);
+    L.wp = o; o = al256(o + pan);
+    L.tws = o; o = al256(o + pan);
     L.mats = o;
     L.nmats = (flags & LLCK_FLAG_DEBUG_KEEP) ? 14 : 6;
     o += (size_t)L.nmats * batch * ld * ld * sizeof(cplx);
@@ -109,7 +115,7 @@ int llck_zgemm(int32_t amode, const void* A, int32_t lda, const void* B, int32_t
     long long z = 0;
     CK(cudaMemcpyAsync(dims, h, sizeof(h), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(off, &z, sizeof(z), cudaMemcpyHostToDevice, st));
-    GemmParams p;
+    GemmParams p = gemm_params_zero();
     p.A = (const cplx*)A; p.strideA = 0; p.lda = lda;
     p.B = (const cplx*)B; p.strideB = 0; p.ldb = ldb;
     p.C = (cplx*)C; p.strideC = 0; p.ldc = ldc;
@@ -244,7 +250,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     }
     TICK();   // 3: finalize+gather done
     // ---- reduced operator ----
-    GemmParams gp;
+    GemmParams gp = gemm_params_zero();
     gp.sig = (const cplx*)signals; gp.sig_off = d_soff;
     // T1 = U^p * Rs
     gp.A = nullptr; gp.strideA = 0; gp.lda = 0;
@@ -263,10 +269,81 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     TICK();   // 4: T1 + Ured done
     // ---- eigen-decomposition of Ured ----
     {
-        size_t sm = (size_t)ld * 16 + 512;
-        CK(cudaFuncSetAttribute(hessenberg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        hessenberg_kernel<<<batch, E_THREADS, sm, st>>>(bH, bZ, stride, ld, d_lv, d_tau);
-        CK(cudaGetLastError());
+        const char* hmode = getenv("LLCK_HESS");
+        if (hmode && hmode[0] == 'u') {
+            size_t sm = (size_t)ld * 16 + 512;
+            CK(cudaFuncSetAttribute(hessenberg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            hessenberg_kernel<<<batch, E_THREADS, sm, st>>>(bH, bZ, stride, ld, d_lv, d_tau);
+            CK(cudaGetLastError());
+        } else {
+            // blocked (compact-WY) reduction: panel kernel + DMMA trailing updates
+            cplx* Vp = (cplx*)(ws + L.vp); cplx* Yp = (cplx*)(ws + L.yp); cplx* VTp = (cplx*)(ws + L.vtp);
+            cplx* Wp = (cplx*)(ws + L.wp); cplx* Tws = (cplx*)(ws + L.tws);
+            const long long pstride = (long long)ld * HB_NB;
+            size_t sm = (size_t)(2 * ld + HB_NB * HB_NB + 4 * HB_NB) * 16 + 512;
+            CK(cudaFuncSetAttribute(hess_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            GemmParams hp = gemm_params_zero();
+            int k0_last = 0;
+            for (int k0 = 0; k0 + 2 < lmax; k0 += HB_NB) {
+                k0_last = k0;
+                hess_panel_kernel<<<batch, E_THREADS, sm, st>>>(bH, stride, ld, d_lv, k0, Vp, Yp, VTp, pstride, Tws, pstride);
+                CK(cudaGetLastError());
+                const int e = k0 + HB_NB;
+                if (e >= lmax) continue;
+                // A[:, e:] -= Y * V[e:, :]^H
+                hp = gemm_params_zero();
+                hp.A = Yp; hp.strideA = pstride; hp.lda = ld;
+                hp.B = Vp + e; hp.strideB = pstride; hp.ldb = ld;
+                hp.C = bH + (long long)ld * e; hp.strideC = stride; hp.ldc = ld;
+                hp.Mv = d_lv; hp.Nv = d_lv; hp.Nc = -e; hp.Kc = HB_NB; hp.accum = 1;
+                CK(zgemm_batched(A_NORMAL, hp, lmax, lmax - e, HB_NB, batch, st, true));
+                // W = (V T)[k0+1:, :]^H * A[k0+1:, e:]
+                hp = gemm_params_zero();
+                hp.A = VTp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
+                hp.B = bH + (k0 + 1) + (long long)ld * e; hp.strideB = stride; hp.ldb = ld;
+                hp.C = Wp; hp.strideC = pstride; hp.ldc = HB_NB;
+                hp.Mc = HB_NB; hp.Nv = d_lv; hp.Nc = -e; hp.Kv = d_lv; hp.Kc = -(k0 + 1);
+                CK(zgemm_batched(A_CONJT, hp, HB_NB, lmax - e, lmax - k0 - 1, batch, st));
+                // A[k0+1:, e:] -= V[k0+1:, :] * W
+                hp = gemm_params_zero();
+                hp.A = Vp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
+                hp.B = Wp; hp.strideB = pstride; hp.ldb = HB_NB;
+                hp.C = bH + (k0 + 1) + (long long)ld * e; hp.strideC = stride; hp.ldc = ld;
+                hp.Mv = d_lv; hp.Mc = -(k0 + 1); hp.Nv = d_lv; hp.Nc = -e; hp.Kc = HB_NB; hp.accum = 1;
+                CK(zgemm_batched(A_NORMAL, hp, lmax - k0 - 1, lmax - e, HB_NB, batch, st));
+            }
+            // Q = P_0 ... P_{n-3}: blocked backward accumulation
+            {
+                dim3 grid(128, batch);
+                set_identity_kernel<<<grid, 256, 0, st>>>(bZ, stride, ld, d_lv);
+                CK(cudaGetLastError());
+            }
+            if (lmax > 2) {
+                for (int k0 = k0_last; k0 >= 0; k0 -= HB_NB) {
+                    hess_qpanel_kernel<<<batch, E_THREADS, 0, st>>>(bH, stride, ld, d_lv, k0, Vp, VTp, pstride, Tws, pstride);
+                    CK(cudaGetLastError());
+                    // W = (V T^H)[k0+1:, :]^H * Q[k0+1:, k0+1:]
+                    hp = gemm_params_zero();
+                    hp.A = VTp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
+                    hp.B = bZ + (k0 + 1) + (long long)ld * (k0 + 1); hp.strideB = stride; hp.ldb = ld;
+                    hp.C = Wp; hp.strideC = pstride; hp.ldc = HB_NB;
+                    hp.Mc = HB_NB; hp.Nv = d_lv; hp.Nc = -(k0 + 1); hp.Kv = d_lv; hp.Kc = -(k0 + 1);
+                    CK(zgemm_batched(A_CONJT, hp, HB_NB, lmax - k0 - 1, lmax - k0 - 1, batch, st));
+                    // Q[k0+1:, k0+1:] -= V[k0+1:, :] * W
+                    hp = gemm_params_zero();
+                    hp.A = Vp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
+                    hp.B = Wp; hp.strideB = pstride; hp.ldb = HB_NB;
+                    hp.C = bZ + (k0 + 1) + (long long)ld * (k0 + 1); hp.strideC = stride; hp.ldc = ld;
+                    hp.Mv = d_lv; hp.Mc = -(k0 + 1); hp.Nv = d_lv; hp.Nc = -(k0 + 1); hp.Kc = HB_NB; hp.accum = 1;
+                    CK(zgemm_batched(A_NORMAL, hp, lmax - k0 - 1, lmax - k0 - 1, HB_NB, batch, st));
+                }
+            }
+            {
+                dim3 grid(128, batch);
+                clear_below_subdiag_kernel<<<grid, 256, 0, st>>>(bH, stride, ld, d_lv);
+                CK(cudaGetLastError());
+            }
+        }
         if (dbg) {
             CK(cudaMemcpyAsync(mat(6), bH, sizeof(cplx) * batch * stride, cudaMemcpyDeviceToDevice, st));
             CK(cudaMemcpyAsync(mat(7), bZ, sizeof(cplx) * batch * stride, cudaMemcpyDeviceToDevice, st));
