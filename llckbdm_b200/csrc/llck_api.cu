@@ -14,6 +14,7 @@
 #include "eig.cuh"
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return -(int)e_; } while (0)
 
@@ -58,7 +59,7 @@ __global__ void mark_unconverged_kernel(const int* done, int* status, int batch)
 
 // ---- workspace layout -----------------------------------------------------------------------------
 struct WsLayout {
-    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, mats, total;
+    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, jws, gws, offws, skip, mats, total;
     int nmats;
 };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -81,6 +82,11 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
     L.vtp = o; o = al256(o + pan);
     L.wp = o; o = al256(o + pan);
     L.tws = o; o = al256(o + pan);
+    const int pairs_max = ((ld / J_B) + 1) / 2 + 1;
+    L.jws = o; o = al256(o + sizeof(cplx) * (size_t)batch * pairs_max * 4096);
+    L.skip = o; o = al256(o + sizeof(int) * (size_t)batch * pairs_max);
+    L.gws = o; o = al256(o + sizeof(cplx) * (size_t)batch * pairs_max * 2080);
+    L.offws = o; o = al256(o + sizeof(double) * (size_t)batch * pairs_max);
     L.mats = o;
     L.nmats = (flags & LLCK_FLAG_DEBUG_KEEP) ? 14 : 6;
     o += (size_t)L.nmats * batch * ld * ld * sizeof(cplx);
@@ -220,19 +226,106 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     int launches = 1;   // svd_init
     const int max_sweeps = 30;
     int h_active = batch;
+    const bool verbose = getenv("LLCK_VERBOSE") != nullptr;
+    double conv2 = 1e-12;   // a member is converged when no pair exceeded 1e-6 (scaled) during a sweep: the sweep leaves <= ~1e-12
+    if (const char* ev = getenv("LLCK_JACOBI_CONV")) { double c = atof(ev); conv2 = c * c; }
+    const char* jmode = getenv("LLCK_JACOBI");
+    const bool fused = (jmode && jmode[0] == 'f');
+    JacobiSplitParams sp;
+    sp.X = bX; sp.V = bV; sp.stride = stride; sp.ld = ld; sp.mv = d_mv; sp.nbv = d_nbv; sp.sweep_off = d_swoff; sp.done = d_done;
+    sp.tol2 = jp.tol2; sp.inner_sweeps = jp.inner_sweeps;
+    sp.Jws = (cplx*)(ws + L.jws); sp.skip = (int*)(ws + L.skip); sp.pairs_max = ((ld / J_B) + 1) / 2 + 1;
+    if (!fused) {
+        CK(cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JS_GRAM_SMEM));
+        CK(cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JS_UPD_SMEM));
+    }
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev2 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    const bool three = !fused && !(jmode && jmode[0] == '2');     // default: gram / eig / update kernels
+    cplx* Gws = (cplx*)(ws + L.gws);
+    double* offws = (double*)(ws + L.offws);
+    if (three) CK(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JE_SMEM));
+    const int nhalf = (!fused && !three && batch >= 8 && getenv("LLCK_JACOBI_2STREAM")) ? 2 : 1;
+    const int bsplit = (nhalf == 2) ? batch / 2 : batch;
+    if (nhalf == 2) {
+        CK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev1, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&evA, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&evB, cudaEventDisableTiming));
+    }
     for (int sweep = 0; sweep < max_sweeps && h_active > 0; ++sweep) {
-        for (int r = 0; r < nbmax - 1; ++r) {
-            jp.round = r;
-            dim3 grid(nbmax / 2, batch);
-            jacobi_step_kernel<<<grid, 256, J_SMEM_BYTES, st>>>(jp);
+        if (nhalf == 2) {   // st2 must see everything issued on st so far (init / previous sweep bookkeeping)
+            CK(cudaEventRecord(ev1, st));
+            CK(cudaStreamWaitEvent(st2, ev1, 0));
         }
-        launches += nbmax - 1 + 1;
+        for (int r = 0; r < nbmax - 1; ++r) {
+            if (fused) {
+                jp.round = r;
+                dim3 grid(nbmax / 2, batch);
+                jacobi_step_kernel<<<grid, 256, J_SMEM_BYTES, st>>>(jp);
+            } else {
+                // two half-batches on two streams: the smem-bound Gram/eigen-solve kernel of one half co-resides with the
+                // DMMA-bound update kernel of the other half (both fit 2 CTAs/SM)
+                // Staggered schedule (cross-stream events): gram(B,r) starts when gram(A,r) is done, gram(A,r+1) when
+                // gram(B,r) is done -> at any time one half is in its eigen-solve while the other is in its DMMA update.
+                auto half_params = [&](int h) {
+                    const int b0 = h ? bsplit : 0;
+                    JacobiSplitParams q = sp;
+                    q.round = r;
+                    q.X = sp.X + (long long)b0 * stride; q.V = sp.V + (long long)b0 * stride;
+                    q.mv = sp.mv + b0; q.nbv = sp.nbv + b0; q.sweep_off = sp.sweep_off + b0; q.done = sp.done + b0;
+                    q.Jws = sp.Jws + (long long)b0 * sp.pairs_max * 4096; q.skip = sp.skip + (long long)b0 * sp.pairs_max;
+                    return q;
+                };
+                const int bnA = bsplit, bnB = batch - bsplit;
+                JacobiSplitParams qa = half_params(0);
+                dim3 gA(nbmax / 2, bnA), gA2(nbmax / 2, bnA, 2);
+                if (three) {
+                    jacobi_gram3_kernel<<<gA, 256, 2 * JS_GTILE * 16, st>>>(qa, Gws, offws);
+                    jacobi_eig_kernel<<<gA, JE_THREADS, JE_SMEM, st>>>(qa, Gws, offws);
+                    jacobi_update_kernel<<<gA2, 256, JS_UPD_SMEM, st>>>(qa);
+                } else {
+                    jacobi_gram_kernel<<<gA, 256, JS_GRAM_SMEM, st>>>(qa);
+                    if (nhalf == 2) {
+                        JacobiSplitParams qb = half_params(1);
+                        dim3 gB(nbmax / 2, bnB), gB2(nbmax / 2, bnB, 2);
+                        CK(cudaEventRecord(evA, st));
+                        CK(cudaStreamWaitEvent(st2, evA, 0));
+                        jacobi_gram_kernel<<<gB, 256, JS_GRAM_SMEM, st2>>>(qb);
+                        CK(cudaEventRecord(evB, st2));
+                        jacobi_update_kernel<<<gA2, 256, JS_UPD_SMEM, st>>>(qa);
+                        CK(cudaStreamWaitEvent(st, evB, 0));
+                        jacobi_update_kernel<<<gB2, 256, JS_UPD_SMEM, st2>>>(qb);
+                    } else {
+                        jacobi_update_kernel<<<gA2, 256, JS_UPD_SMEM, st>>>(qa);
+                    }
+                }
+            }
+        }
+        if (!fused && nhalf == 2) {
+            CK(cudaEventRecord(ev2, st2));
+            CK(cudaStreamWaitEvent(st, ev2, 0));
+        }
+        launches += fused ? (nbmax - 1 + 1) : ((three ? 3 : 2 * nhalf) * (nbmax - 1) + 1);
         CK(cudaGetLastError());
+        if (verbose) {
+            unsigned long long* h = (unsigned long long*)malloc(sizeof(unsigned long long) * batch);
+            CK(cudaMemcpyAsync(h, d_swoff, sizeof(unsigned long long) * batch, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            double mx = 0.0, mn = 1e300;
+            for (int b = 0; b < batch; ++b) { double v; memcpy(&v, &h[b], 8); v = sqrt(v); if (v > mx) mx = v; if (v < mn) mn = v; }
+            fprintf(stderr, "[llck] jacobi sweep %d: active=%d  max off (pre-rotation) over members: max=%.3e min=%.3e\n", sweep, h_active, mx, mn);
+            free(h);
+        }
         CK(cudaMemsetAsync(d_nact, 0, sizeof(int), st));
-        jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, d_nact, batch, 1e-14);
+        jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, d_nact, batch, conv2);
         CK(cudaMemcpyAsync(&h_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ++sweeps_run;
+    }
+    if (nhalf == 2) {
+        cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(evA); cudaEventDestroy(evB); cudaStreamDestroy(st2);
     }
     TICK();   // 2: jacobi done
     if (h_active > 0) {
