@@ -9,7 +9,7 @@ Hankel dimension m = 1024, l = m, p = 1, q = 0  (BASELINE.json: "KBDM solves/sec
   value     whole-job solves/s with the FIDs already resident in HBM (CUDA events, max over ranks)
   e2e       the same through the public host API (ensemble.solve_ensemble: host FIDs in, host line lists out;
             H2D + D2H inside the timed region)
-  roofline  dominant kernel (jacobi_step_kernel): algorithmic FP64 flops per launch / measured launch time
+  roofline  dominant kernel (jacobi_update_kernel): algorithmic FP64 flops per launch / measured launch time
             vs the FP64 tensor (DMMA) peak measured on this pool (profiles/fp64_peak_r01.json -- MEASURED_PEAKS.json
             carries no FP64 figure)
   cpu_baseline  the numpy/scipy restatement of the reference (oracle/, kind "port") timed on the host cores
@@ -112,6 +112,17 @@ def cpu_reference_solve(m, how):
     return time.perf_counter() - t0
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU reference must run on all host cores, so lift the BLAS limits."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -124,6 +135,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import scipy.linalg  # noqa: F401  (load BLAS before lifting the thread limits)
+    use_all_host_threads()
     m = args.m
     for _ in range(args.warmup):
         cpu_reference_solve(m, "einsum")
@@ -194,12 +207,14 @@ def run_native(args):
     e0.record()
     stage_us = np.zeros(9)
     launches = jac_launches = 0
+    upd_us = []
     for _ in range(args.steps):
         last = ensemble.solve_device(sig_dev, offsets, ms, ms, 1, 0.0, DWELL, workspace=ws, flags=_native.FLAG_TIMING)
         info = last["info"]
         stage_us += np.array(info[4:13], dtype=float)
         launches += info[13]
         jac_launches += info[14]
+        upd_us.append(info[15])
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -229,8 +244,10 @@ def run_native(args):
     # ---- roofline of the dominant kernel (block-Jacobi SVD step) ----
     peak, peak_src = fp64_peak_tflops()
     nb = 2 * ((m + 63) // 64)
-    flops_per_launch = 80.0 * 32 * 32 * m * (nb // 2) * batch       # Gram 16 b^2 m + update of X and V 2 x 32 b^2 m per pair
-    jac_s_per_launch = (stage_us[1] * 1e-6) / max(jac_launches, 1)
+    # dominant kernel: jacobi_update_kernel (Xp <- Xp J and Vp <- Vp J for every pair of a round): 2 x 32 b^2 m flop per pair,
+    # duration = CUDA events around every launch inside the timed region (info[15], averaged over the steps)
+    flops_per_launch = 64.0 * 32 * 32 * m * (nb // 2) * batch
+    jac_s_per_launch = float(np.mean(upd_us)) * 1e-6 if np.mean(upd_us) > 0 else (stage_us[1] * 1e-6) / max(jac_launches, 1)
     achieved = flops_per_launch / jac_s_per_launch / 1e12
     alg_flops = ensemble.flops_per_solve(m, m) * batch * args.steps
     names = ["init", "jacobi_svd", "finalize_gather", "gemm_T1_Ured", "hessenberg", "hqr", "trevc", "gemm_P_B_W", "epilogue"]
@@ -245,7 +262,7 @@ def run_native(args):
         "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "jacobi_step_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "tensor", "kernel": "jacobi_update_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "launches": int(jac_launches), "avg_launch_ms": jac_s_per_launch * 1e3,
                      "algorithmic_flops_per_launch": flops_per_launch},
@@ -267,6 +284,8 @@ def run_native(args):
         out["llc_ensemble_c2"] = {"members": 100, "m_range": "700..1024", "solve_phase_s": time.perf_counter() - t0,
                                   "bad_status_members": int((r2.status != 0).sum()), "note": "host FID in, host line lists out; HDBSCAN clustering not included"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import scipy.linalg  # noqa: F401
+        use_all_host_threads()
         cores = blas_threads()
         t_ref = cpu_reference_solve(m, "einsum")
         t_tuned = cpu_reference_solve(m, "gemm")

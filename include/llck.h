@@ -71,7 +71,8 @@ size_t llck_debug_offset(int batch, int ld, int which);
  *   info       [host] int32   [16] (optional)      [0]=Jacobi sweeps run, [1]=max QR multishift sweeps, [2]=ld, [3]=nbmax,
  *                                                  [4..12]=stage durations in us when LLCK_FLAG_TIMING (init, jacobi,
  *                                                  finalize+gather, T1+Ured, hessenberg, hqr, trevc, P+B+W, epilogue),
- *                                                  [13]=kernel launches issued, [14]=jacobi_step_kernel launches
+ *                                                  [13]=kernel launches issued, [14]=Jacobi rounds run,
+ *                                                  [15]=average jacobi_update_kernel duration in us (LLCK_FLAG_TIMING)
  */
 int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int32_t* m, const int32_t* l,
                       int32_t p, double q, double dwell, int32_t batch,

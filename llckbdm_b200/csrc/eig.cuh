@@ -699,3 +699,76 @@ __global__ void __launch_bounds__(E_THREADS, 1) trevc_kernel(const cplx* Tm, cpl
     }
     (void)red;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Blocked trevc: X (upper triangular eigenvector matrix of T) by block back substitution.
+// For the 32-row block [j0, j0+32): trevc_diag_kernel solves, for every column k >= j0, the small shifted triangular
+// system inside the block (one thread per column, block of T in shared memory); the rows above the block are then
+// updated for all columns at once by the batched DMMA GEMM   X[0:j0, j0:n] -= T[0:j0, j0:j1] * X[j0:j1, j0:n].
+// X must be zero-initialised (trevc_zero_kernel); the unit diagonal is written by the diag kernel.
+// ---------------------------------------------------------------------------------------------
+#define TV_NB 32
+__global__ void trevc_zero_kernel(cplx* X, long long stride, int ld, const int* lv) {
+    const int b = blockIdx.y, n = lv[b];
+    cplx* Xb = X + (long long)b * stride;
+    const long long total = (long long)ld * n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+        Xb[idx] = mkc(0.0, 0.0);
+}
+
+__global__ void __launch_bounds__(128) trevc_diag_kernel(const cplx* Tm, cplx* X, long long stride, int ld, const int* lv, int j0) {
+    __shared__ cplx Tblk[TV_NB][TV_NB + 1];
+    const int b = blockIdx.y, n = lv[b];
+    if (j0 >= n) return;
+    const cplx* Tb = Tm + (long long)b * stride;
+    cplx* Xb = X + (long long)b * stride;
+    const int j1 = min(j0 + TV_NB, n), nr = j1 - j0;
+    for (int idx = threadIdx.x; idx < TV_NB * TV_NB; idx += blockDim.x) {
+        int r = idx % TV_NB, c = idx / TV_NB;
+        Tblk[r][c] = (r < nr && c < nr && r <= c) ? Tb[(j0 + r) + (long long)ld * (j0 + c)] : mkc(0.0, 0.0);
+    }
+    __syncthreads();
+    const int k = j0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const cplx tkk = Tb[k + (long long)ld * k];
+    const double smlnum = LLCK_SAFMIN * ((double)n / LLCK_EPS);
+    const double smin = fmax(LLCK_EPS * cabs1(tkk), smlnum);
+    cplx* xc = Xb + (long long)ld * k + j0;
+    cplx x[TV_NB];
+#pragma unroll
+    for (int r = 0; r < TV_NB; ++r) x[r] = (r < nr) ? xc[r] : mkc(0.0, 0.0);
+    const int rtop = min(nr - 1, k - j0);      // rows below k (inside the block) stay zero
+#pragma unroll
+    for (int r = TV_NB - 1; r >= 0; --r) {
+        if (r <= rtop) {
+            cplx xr;
+            if (j0 + r == k) xr = mkc(1.0, 0.0);
+            else {
+                cplx d = csub(Tblk[r][r], tkk);
+                if (cabs1(d) < smin) d = mkc(smin, 0.0);
+                xr = cdiv(x[r], d);
+            }
+            x[r] = xr;
+#pragma unroll
+            for (int q = 0; q < TV_NB; ++q)
+                if (q < r) x[q] = csub(x[q], cmul(xr, Tblk[q][r]));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < TV_NB; ++r)
+        if (r <= rtop) xc[r] = x[r];
+}
+
+__global__ void trevc_normalize_kernel(cplx* X, long long stride, int ld, const int* lv) {
+    const int b = blockIdx.y, n = lv[b];
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= n) return;
+    cplx* xc = X + (long long)b * stride + (long long)ld * k;
+    double mx = 0.0;
+    for (int i = lane; i <= k; i += 32) mx = fmax(mx, cabs1(xc[i]));
+    mx = warp_max(mx);
+    if (mx > 0.0 && isfinite(mx)) {
+        const double sc = 1.0 / mx;
+        for (int i = lane; i <= k; i += 32) xc[i] = cscale(xc[i], sc);
+    }
+}

@@ -21,6 +21,7 @@ struct GemmParams {
     const int* Mv; const int* Nv; const int* Kv;     // per-member dims (device arrays, length batch; may be null)
     int Mc, Nc, Kc;                                  // constants added to the per-member dims (dims = v[b] + c)
     int accum;                                       // 0: C = A*B ; 1: C -= A*B
+    int Kcap;                                        // if > 0: K = min(K, Kcap)
     // Hankel source
     const cplx* sig; const long long* sig_off; int shift;
 };
@@ -28,7 +29,7 @@ struct GemmParams {
 static inline GemmParams gemm_params_zero() {
     GemmParams p;
     p.A = nullptr; p.strideA = 0; p.lda = 0; p.B = nullptr; p.strideB = 0; p.ldb = 0; p.C = nullptr; p.strideC = 0; p.ldc = 0;
-    p.Mv = p.Nv = p.Kv = nullptr; p.Mc = p.Nc = p.Kc = 0; p.accum = 0; p.sig = nullptr; p.sig_off = nullptr; p.shift = 0;
+    p.Mv = p.Nv = p.Kv = nullptr; p.Mc = p.Nc = p.Kc = 0; p.accum = 0; p.Kcap = 0; p.sig = nullptr; p.sig_off = nullptr; p.shift = 0;
     return p;
 }
 
@@ -48,7 +49,9 @@ __global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* smem = reinterpret_cast<cplx*>(smem_raw);
     const int b = blockIdx.z;
-    const int M = (p.Mv ? p.Mv[b] : 0) + p.Mc, N = (p.Nv ? p.Nv[b] : 0) + p.Nc, K = (p.Kv ? p.Kv[b] : 0) + p.Kc;
+    const int M = (p.Mv ? p.Mv[b] : 0) + p.Mc, N = (p.Nv ? p.Nv[b] : 0) + p.Nc;
+    int K = (p.Kv ? p.Kv[b] : 0) + p.Kc;
+    if (p.Kcap > 0 && K > p.Kcap) K = p.Kcap;
     const int row0 = blockIdx.x * G_BM, col0 = blockIdx.y * G_BN;
     if (row0 >= M || col0 >= N || K <= 0) return;
 

@@ -239,6 +239,9 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         CK(cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JS_GRAM_SMEM));
         CK(cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JS_UPD_SMEM));
     }
+    cudaEvent_t uev[128];
+    double upd_us = 0.0; int upd_launches = 0;
+    if (timing) for (int i = 0; i < 128; ++i) CK(cudaEventCreate(&uev[i]));
     cudaStream_t st2 = nullptr;
     cudaEvent_t ev2 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
     const bool three = !fused && !(jmode && jmode[0] == '2');     // default: gram / eig / update kernels
@@ -284,7 +287,9 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
                 if (three) {
                     jacobi_gram3_kernel<<<gA, 256, 2 * JS_GTILE * 16, st>>>(qa, Gws, offws);
                     jacobi_eig_kernel<<<gA, JE_THREADS, JE_SMEM, st>>>(qa, Gws, offws);
+                    if (timing && r < 64) CK(cudaEventRecord(uev[2 * r], st));
                     jacobi_update_kernel<<<gA2, 256, JS_UPD_SMEM, st>>>(qa);
+                    if (timing && r < 64) CK(cudaEventRecord(uev[2 * r + 1], st));
                 } else {
                     jacobi_gram_kernel<<<gA, 256, JS_GRAM_SMEM, st>>>(qa);
                     if (nhalf == 2) {
@@ -323,7 +328,15 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         CK(cudaMemcpyAsync(&h_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ++sweeps_run;
+        if (timing && three) {
+            for (int r = 0; r < nbmax - 1 && r < 64; ++r) {
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, uev[2 * r], uev[2 * r + 1]));
+                upd_us += 1000.0 * ms; ++upd_launches;
+            }
+        }
     }
+    if (timing) for (int i = 0; i < 128; ++i) cudaEventDestroy(uev[i]);
     if (nhalf == 2) {
         cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(evA); cudaEventDestroy(evB); cudaStreamDestroy(st2);
     }
@@ -446,10 +459,34 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs);
         CK(cudaGetLastError());
         TICK();   // 6: hqr done
-        size_t sm2 = (size_t)ld * 32 + 512;
-        CK(cudaFuncSetAttribute(trevc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-        trevc_kernel<<<batch, E_THREADS, sm2, st>>>(bH, bXev, stride, ld, d_lv);
-        CK(cudaGetLastError());
+        const char* tmode = getenv("LLCK_TREVC");
+        if (tmode && tmode[0] == 'u') {
+            size_t sm2 = (size_t)ld * 32 + 512;
+            CK(cudaFuncSetAttribute(trevc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            trevc_kernel<<<batch, E_THREADS, sm2, st>>>(bH, bXev, stride, ld, d_lv);
+            CK(cudaGetLastError());
+        } else {
+            dim3 gz(128, batch);
+            trevc_zero_kernel<<<gz, 256, 0, st>>>(bXev, stride, ld, d_lv);
+            CK(cudaGetLastError());
+            for (int j0 = ((lmax - 1) / TV_NB) * TV_NB; j0 >= 0; j0 -= TV_NB) {
+                dim3 gd((lmax - j0 + 127) / 128, batch);
+                trevc_diag_kernel<<<gd, 128, 0, st>>>(bH, bXev, stride, ld, d_lv, j0);
+                CK(cudaGetLastError());
+                if (j0 > 0) {
+                    // X[0:j0, j0:n] -= T[0:j0, j0:j0+32] * X[j0:j0+32, j0:n]
+                    GemmParams tp = gemm_params_zero();
+                    tp.A = bH + (long long)ld * j0; tp.strideA = stride; tp.lda = ld;
+                    tp.B = bXev + j0 + (long long)ld * j0; tp.strideB = stride; tp.ldb = ld;
+                    tp.C = bXev + (long long)ld * j0; tp.strideC = stride; tp.ldc = ld;
+                    tp.Mc = j0; tp.Nv = d_lv; tp.Nc = -j0; tp.Kv = d_lv; tp.Kc = -j0; tp.Kcap = TV_NB; tp.accum = 1;
+                    CK(zgemm_batched(A_NORMAL, tp, j0, lmax - j0, TV_NB, batch, st));
+                }
+            }
+            dim3 gn((lmax + 7) / 8, batch);
+            trevc_normalize_kernel<<<gn, 256, 0, st>>>(bXev, stride, ld, d_lv);
+            CK(cudaGetLastError());
+        }
     }
     TICK();   // 7: trevc done
     // P = Z * Xev
@@ -488,7 +525,8 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         }
         info[0] = sweeps_run; info[1] = h_maxs; info[2] = ld; info[3] = nbmax;
         info[13] = launches + 2 /*finalize, gather*/ + 5 /*gemms*/ + 3 /*hessenberg, hqr, trevc*/ + 1 /*epilogue*/;
-        info[14] = sweeps_run * (nbmax - 1);   // jacobi_step_kernel launches
+        info[14] = sweeps_run * (nbmax - 1);   // Jacobi rounds (one gram + eig + update launch each)
+        info[15] = (upd_launches > 0) ? (int32_t)(upd_us / upd_launches) : 0;   // avg jacobi_update_kernel duration (us), timing mode
     }
     CK(cudaStreamSynchronize(st));
     if (timing) {
