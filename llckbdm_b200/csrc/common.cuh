@@ -59,19 +59,23 @@ __host__ __device__ __forceinline__ cplx csqrt_(cplx z) {
 
 // Givens rotation: c real, s complex with [c s; -conj(s) c] * [a; b] = [r; 0]   (LAPACK zlartg convention)
 __host__ __device__ __forceinline__ void givens(cplx a, cplx b, double& c, cplx& s) {
-    double nb = cabs2(b);
+    const double nb = cabs2(b);
     if (nb == 0.0) { c = 1.0; s = mkc(0.0, 0.0); return; }
-    double na2 = cabs2(a);
+    const double na2 = cabs2(a);
     if (na2 == 0.0) {
-        double ab = sqrt(nb);
+        const double ab = sqrt(nb);
         c = 0.0; s = mkc(b.x / ab, -b.y / ab);   // conj(b)/|b|
         return;
     }
-    double na = sqrt(na2);
-    double nrm = sqrt(na2 + nb);
-    c = na / nrm;
-    double f = 1.0 / (na * nrm);
-    cplx ab = cmul(a, cconj(b));     // a * conj(b)
+    // c = |a|/nrm, s = a conj(b) / (|a| nrm): two reciprocal square roots, no division
+#ifdef __CUDA_ARCH__
+    const double ra = rsqrt(na2), rn = rsqrt(na2 + nb);
+#else
+    const double ra = 1.0 / sqrt(na2), rn = 1.0 / sqrt(na2 + nb);
+#endif
+    c = na2 * ra * rn;
+    const double f = ra * rn;
+    const cplx ab = cmul(a, cconj(b));     // a * conj(b)
     s = mkc(ab.x * f, ab.y * f);
 }
 

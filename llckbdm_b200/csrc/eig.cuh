@@ -239,9 +239,11 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
             const int len = n - c - 1;
             cplx y0 = mkc(0.0, 0.0), y1 = mkc(0.0, 0.0), y2 = mkc(0.0, 0.0), y3 = mkc(0.0, 0.0);
             int q = 0;
-            for (; q + 3 < len; q += 4) {
+            for (; q + 7 < len; q += 8) {
                 cplx a0 = row[(long long)ld * q], a1 = row[(long long)ld * (q + 1)], a2 = row[(long long)ld * (q + 2)], a3 = row[(long long)ld * (q + 3)];
+                cplx a4 = row[(long long)ld * (q + 4)], a5 = row[(long long)ld * (q + 5)], a6 = row[(long long)ld * (q + 6)], a7 = row[(long long)ld * (q + 7)];
                 y0 = cfma(a0, vv[q], y0); y1 = cfma(a1, vv[q + 1], y1); y2 = cfma(a2, vv[q + 2], y2); y3 = cfma(a3, vv[q + 3], y3);
+                y0 = cfma(a4, vv[q + 4], y0); y1 = cfma(a5, vv[q + 5], y1); y2 = cfma(a6, vv[q + 6], y2); y3 = cfma(a7, vv[q + 7], y3);
             }
             for (; q < len; ++q) y0 = cfma(row[(long long)ld * q], vv[q], y0);
             cplx y = cadd(cadd(y0, y1), cadd(y2, y3));
@@ -328,7 +330,7 @@ __device__ __forceinline__ bool negligible_sub(cplx sub, cplx d0, cplx d1) {
     return h <= LLCK_EPS * tst;
 }
 
-__device__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, int n, int wrows) {
+__device__ __noinline__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, int n, int wrows) {
     const int lane = threadIdx.x & 31;
     int ihi = n - 1, its = 0, total = 0;
     while (ihi >= 0) {
@@ -394,9 +396,30 @@ __device__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, int n, int wr
 //   H[ws:we, we:n] <- Ww^H H[ws:we, we:n];  H[0:ws, ws:we] <- H[0:ws, ws:we] Ww;  Z[:, ws:we] <- Z[:, ws:we] Ww
 // all E_THREADS threads participate; tiles: 2 x E_TILE double buffer
 // ---------------------------------------------------------------------------------------------
-__device__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, int n, int ws, int we, const cplx* Ww, cplx* tiles) {
+__device__ __noinline__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, int n, int ws, int we, const cplx* Ww, cplx* tiles, int* kr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int ww = we - ws;
+    // W is a product of plane rotations: every column has a limited range of nonzero rows.  kr[2J], kr[2J+1] = first/last+1
+    // row (multiples of 4) holding a nonzero in column tile J (8 columns); the DMMA k-loops below skip the exact zeros.
+    __syncthreads();
+    if (tid < 64) {
+        int lo = 64, hi = 0;
+        for (int k = 0; k < E_W; ++k) {
+            cplx v = Ww[k + E_LDW * tid];
+            if (v.x != 0.0 || v.y != 0.0) { if (k < lo) lo = k; hi = k + 1; }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((tid & 7) == 0) {
+            if (lo >= hi) { lo = 0; hi = 4; }
+            kr[2 * (tid >> 3)] = lo & ~3;
+            kr[2 * (tid >> 3) + 1] = (hi + 3) & ~3;
+        }
+    }
+    __syncthreads();
     // ---- row strip ----
     {
         const int ncols = n - we;
@@ -423,7 +446,10 @@ __device__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, int n, int ws
             const cplx* T = tiles + buf * E_TILE;
             double acc[1][2][4];
             zero_acc<1, 2>(acc);
-            warp_zmma<1, 2, true, false>(acc, Ww + E_LDW * (8 * wr), E_LDW, 1, T + 68 * (16 * wc), 1, 68, E_W);
+            {
+                const int klo = kr[2 * wr], khi = kr[2 * wr + 1];
+                warp_zmma<1, 2, true, false>(acc, Ww + E_LDW * (8 * wr) + klo, E_LDW, 1, T + 68 * (16 * wc) + klo, 1, 68, khi - klo);
+            }
             const int row = 8 * wr + g;
             if (row < ww) {
                 const int c0 = we + tl * 32 + 16 * wc;
@@ -464,7 +490,10 @@ __device__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, int n, int ws
             const cplx* T = tiles + buf * E_TILE;
             double acc[1][2][4];
             zero_acc<1, 2>(acc);
-            warp_zmma<1, 2, false, false>(acc, T + 8 * wr, 1, 34, Ww + E_LDW * (16 * wc), 1, E_LDW, E_W);
+            {
+                const int klo = min(kr[4 * wc], kr[4 * wc + 2]), khi = max(kr[4 * wc + 1], kr[4 * wc + 3]);
+                warp_zmma<1, 2, false, false>(acc, T + 8 * wr + 34 * klo, 1, 34, Ww + E_LDW * (16 * wc) + klo, 1, E_LDW, khi - klo);
+            }
             const int row = tl * 32 + 8 * wr + g;
             if (row < nrows) {
 #pragma unroll
@@ -491,7 +520,7 @@ __device__ __forceinline__ int block_max_int(int v, int* scratch) {
 }
 
 // status: 0 ok, 1 = QR did not converge
-__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out) {
+__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out, long long* prof) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* Hw = reinterpret_cast<cplx*>(smem_raw);
     cplx* Ww = Hw + E_MAT;
@@ -506,6 +535,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
 
     int ihi = n - 1, its = 0, nsweeps = 0;
     bool failed = false;
+    long long tp[6] = {0, 0, 0, 0, 0, 0};   // scan+shifts, window load, chase, store, strips, small blocks
+    long long tc = clock64();
+#define PROF(i) do { if (prof) { long long tn_ = clock64(); tp[i] += tn_ - tc; tc = tn_; } } while (0)
     while (ihi >= 0) {
         __syncthreads();
         // ---- deflation scan: largest k in [1, ihi] with negligible H[k,k-1] ----
@@ -533,11 +565,13 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             }
             __syncthreads();
             if (iscr[32] < 0) { failed = true; break; }
+            PROF(5);
             for (int idx = tid; idx < size * size; idx += E_THREADS) {
                 int r = idx % size, c = idx / size;
                 Hb[(ilo + r) + (long long)ld * (ilo + c)] = Hw[r + E_LDW * c];
             }
-            apply_window_transform(Hb, Zb, ld, n, ilo, ihi + 1, Ww, tiles);
+            apply_window_transform(Hb, Zb, ld, n, ilo, ihi + 1, Ww, tiles, iscr + 40);
+            PROF(4);
             ihi = ilo - 1; its = 0;
             continue;
         }
@@ -569,6 +603,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             if (iscr[32] < 0) { failed = true; break; }
         }
         // ---- one multishift sweep over [ilo, ihi] ----
+        PROF(0);
         ++nsweeps;
         int tstep = 0;
         while (true) {
@@ -589,6 +624,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 Ww[r + E_LDW * c] = mkc(r == c ? 1.0 : 0.0, 0.0);
             }
             __syncthreads();
+            PROF(1);
             for (int step = 0; step < T; ++step) {
                 const int p = ilo - 1 - 2 * warp + tstep + step;     // this warp's bulge
                 const bool active = (p >= ilo - 1) && (p <= ihi - 2);
@@ -628,18 +664,23 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 }
                 __syncthreads();
             }
+            PROF(2);
             for (int idx = tid; idx < ww * ww; idx += E_THREADS) {
                 int r = idx % ww, c = idx / ww;
                 Hb[(ws + r) + (long long)ld * (ws + c)] = Hw[r + E_LDW * c];
             }
-            apply_window_transform(Hb, Zb, ld, n, ws, we, Ww, tiles);
+            PROF(3);
+            apply_window_transform(Hb, Zb, ld, n, ws, we, Ww, tiles, iscr + 40);
+            PROF(4);
             tstep += T;
         }
     }
     if (tid == 0) {
         if (failed) atomicMax(&status[b], 1);
         if (sweeps_out) sweeps_out[b] = nsweeps;
+        if (prof) for (int i = 0; i < 6; ++i) prof[6 * b + i] = tp[i];
     }
+#undef PROF
 }
 
 // ---------------------------------------------------------------------------------------------

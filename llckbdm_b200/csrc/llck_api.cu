@@ -456,8 +456,20 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         }
         TICK();   // 5: hessenberg done
         CK(cudaFuncSetAttribute(hqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HQR_SMEM_BYTES));
-        hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs);
+        long long* d_prof = nullptr;
+        if (verbose) { CK(cudaMalloc(&d_prof, sizeof(long long) * 6 * batch)); }
+        hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof);
         CK(cudaGetLastError());
+        if (verbose) {
+            long long* hp = (long long*)malloc(sizeof(long long) * 6 * batch);
+            CK(cudaMemcpyAsync(hp, d_prof, sizeof(long long) * 6 * batch, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            double tot[6] = {0, 0, 0, 0, 0, 0};
+            for (int b = 0; b < batch; ++b) for (int i = 0; i < 6; ++i) tot[i] += (double)hp[6 * b + i] / batch;
+            fprintf(stderr, "[llck] hqr phase Mcycles/member: scan+shifts=%.1f load=%.1f chase=%.1f store=%.1f strips=%.1f small=%.1f\n",
+                    tot[0] / 1e6, tot[1] / 1e6, tot[2] / 1e6, tot[3] / 1e6, tot[4] / 1e6, tot[5] / 1e6);
+            free(hp); cudaFree(d_prof);
+        }
         TICK();   // 6: hqr done
         const char* tmode = getenv("LLCK_TREVC");
         if (tmode && tmode[0] == 'u') {

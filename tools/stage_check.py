@@ -42,7 +42,7 @@ def main():
     sigma = float(sys.argv[5]) if len(sys.argv) > 5 else 1e-3
     dwell = 5e-4
     lib = _native.load()
-    sigs = [brain_sim(2048, sigma, seed=i) for i in range(len(ms))]
+    sigs = [brain_sim(max(2048, 2 * max(ms) + 8), sigma, seed=i) for i in range(len(ms))]
     ls = [m if lsel < 0 else min(lsel, m) for m in ms]
     flat, offs = ensemble.flatten_signals(sigs, len(ms))
     dev = torch.device("cuda:0")
