@@ -144,35 +144,62 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // A element (i,k) at A[i*a_si + k*a_sk]; B element (k,j) at B[k*b_sk + j*b_sj]  (shared memory, complex128).
 // acc[i][j][0..1] = Re of (row g, cols 2t, 2t+1) of tile (i,j); acc[i][j][2..3] = Im.
 template <int MT, int NT, bool CONJA, bool CONJB>
+__device__ __forceinline__ void zmma_load_frags(cplx (&a)[MT], cplx (&b)[NT], const cplx* __restrict__ ap, int a_si, int a_sk,
+                                                const cplx* __restrict__ bp, int b_sk, int b_sj, int k) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        a[i] = ap[(8 * i) * a_si + k * a_sk];
+        if (CONJA) a[i].y = -a[i].y;
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        b[j] = bp[k * b_sk + (8 * j) * b_sj];
+        if (CONJB) b[j].y = -b[j].y;
+    }
+}
+
+// 4 real DMMAs per complex tile product, issued as two passes over all tiles so that the two DMMAs that hit the same
+// accumulator pair are 2*MT*NT instructions apart (the dependent-issue latency of DMMA is long).
+template <int MT, int NT>
+__device__ __forceinline__ void zmma_compute(double (&acc)[MT][NT][4], const cplx (&a)[MT], const cplx (&b)[NT]) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+            dmma(acc[i][j][2], acc[i][j][3], a[i].x, b[j].y);
+        }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const double nai = -a[i].y;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            dmma(acc[i][j][0], acc[i][j][1], nai, b[j].y);
+            dmma(acc[i][j][2], acc[i][j][3], a[i].y, b[j].x);
+        }
+    }
+}
+
+template <int MT, int NT, bool CONJA, bool CONJB>
 __device__ __forceinline__ void warp_zmma(double (&acc)[MT][NT][4], const cplx* __restrict__ A, int a_si, int a_sk,
                                           const cplx* __restrict__ B, int b_sk, int b_sj, int kcount) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const cplx* ap = A + g * a_si + t * a_sk;
     const cplx* bp = B + t * b_sk + g * b_sj;
-#pragma unroll 2
-    for (int k = 0; k < kcount; k += 4) {
-        cplx a[MT], b[NT];
-#pragma unroll
-        for (int i = 0; i < MT; ++i) {
-            a[i] = ap[(8 * i) * a_si + k * a_sk];
-            if (CONJA) a[i].y = -a[i].y;
-        }
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            b[j] = bp[k * b_sk + (8 * j) * b_sj];
-            if (CONJB) b[j].y = -b[j].y;
-        }
-#pragma unroll
-        for (int i = 0; i < MT; ++i) {
-            const double nai = -a[i].y;
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
-                dmma(acc[i][j][2], acc[i][j][3], a[i].x, b[j].y);
-                dmma(acc[i][j][0], acc[i][j][1], nai, b[j].y);
-                dmma(acc[i][j][2], acc[i][j][3], a[i].y, b[j].x);
-            }
-        }
+    if (kcount <= 0) return;
+    // fragments are double-buffered in registers: the LDS.128 of step k+4 are in flight while step k's DMMAs issue
+    cplx a0[MT], b0[NT], a1[MT], b1[NT];
+    zmma_load_frags<MT, NT, CONJA, CONJB>(a0, b0, ap, a_si, a_sk, bp, b_sk, b_sj, 0);
+    int k = 0;
+    while (true) {
+        if (k + 4 < kcount) zmma_load_frags<MT, NT, CONJA, CONJB>(a1, b1, ap, a_si, a_sk, bp, b_sk, b_sj, k + 4);
+        zmma_compute<MT, NT>(acc, a0, b0);
+        k += 4;
+        if (k >= kcount) break;
+        if (k + 4 < kcount) zmma_load_frags<MT, NT, CONJA, CONJB>(a0, b0, ap, a_si, a_sk, bp, b_sk, b_sj, k + 4);
+        zmma_compute<MT, NT>(acc, a1, b1);
+        k += 4;
+        if (k >= kcount) break;
     }
 }
 

@@ -480,7 +480,9 @@ __device__ __noinline__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, 
             }
             cp_async_commit();
         };
-        const int wr = warp >> 2, wc = warp & 3;
+        // warps w, w+4, w+8, w+12 share one SM sub-partition (and its DMMA pipe): give each sub-partition all four column
+        // groups (their k-ranges differ) so that the four pipes carry equal work
+        const int wr = warp >> 2, wc = (warp + (warp >> 2)) & 3;
         if (ntiles > 0) load(0, 0);
         for (int tl = 0; tl < ntiles; ++tl) {
             const int buf = tl & 1;

@@ -469,6 +469,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             fprintf(stderr, "[llck] hqr phase Mcycles/member: scan+shifts=%.1f load=%.1f chase=%.1f store=%.1f strips=%.1f small=%.1f\n",
                     tot[0] / 1e6, tot[1] / 1e6, tot[2] / 1e6, tot[3] / 1e6, tot[4] / 1e6, tot[5] / 1e6);
             free(hp); cudaFree(d_prof);
+
         }
         TICK();   // 6: hqr done
         const char* tmode = getenv("LLCK_TREVC");
