@@ -392,6 +392,151 @@ __device__ __noinline__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Aggressive early deflation (Braman-Byers-Mathias), executed by ONE warp on the trailing nw x nw window held in shared
+// memory: T (Hessenberg on entry), V = I on entry.  s = H[kwtop, kwtop-1] is the spike scale.
+//   1. Schur-decompose the window (T <- V^H T V upper triangular).
+//   2. From the bottom: eigenvalue k is deflatable if |s V[0,k]| <= eps |T[k,k]|; undeflatable ones are swapped to the top.
+//   3. The ns undeflated eigenvalues become the shifts of the next multishift sweep.
+//   4. If anything deflated (or s == 0): reflect the spike s*conj(V[0,0:ns]) back to a single entry, restore the leading
+//      ns x ns block to Hessenberg form (transformations accumulated in V); the caller writes T back and applies V.
+// Returns ns (>= 0), or -1 if the window QR failed.  out[0] = 1 if T/V must be written back.  newsub = new H[kwtop,kwtop-1].
+// ---------------------------------------------------------------------------------------------
+#define E_NW 32
+__device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shifts, cplx* vbuf, int* out, cplx* newsub) {
+    const int lane = threadIdx.x & 31;
+    const int L = E_LDW;
+    if (warp_small_hqr(T, L, V, L, nw, nw) < 0) return -1;
+    __syncwarp();
+    int ns = nw, ilst = 0;
+    const double s1 = cabs1(s);
+    const double smallnum = LLCK_SAFMIN / LLCK_EPS;
+    for (int knt = 0; knt < nw; ++knt) {
+        if (ilst >= ns) break;
+        double foo = cabs1(T[(ns - 1) + L * (ns - 1)]);
+        if (foo == 0.0) foo = s1;
+        if (s1 * cabs1(V[0 + L * (ns - 1)]) <= fmax(smallnum, LLCK_EPS * foo)) {
+            --ns;
+        } else {
+            // move T[ns-1,ns-1] up to position ilst by adjacent swaps
+            for (int k = ns - 2; k >= ilst; --k) {
+                const cplx t11 = T[k + L * k], t22 = T[(k + 1) + L * (k + 1)];
+                double c; cplx sn;
+                givens(T[k + L * (k + 1)], csub(t22, t11), c, sn);
+                const cplx csn = cconj(sn);
+                __syncwarp();
+                for (int col = k + 2 + lane; col < nw; col += 32) {
+                    cplx a = T[k + L * col], bq = T[(k + 1) + L * col];
+                    T[k + L * col] = cadd(cscale(a, c), cmul(sn, bq));
+                    T[(k + 1) + L * col] = csub(cscale(bq, c), cmul(csn, a));
+                }
+                for (int row = lane; row < k; row += 32) {
+                    cplx a = T[row + L * k], bq = T[row + L * (k + 1)];
+                    T[row + L * k] = cadd(cscale(a, c), cmul(csn, bq));
+                    T[row + L * (k + 1)] = csub(cscale(bq, c), cmul(sn, a));
+                }
+                for (int row = lane; row < nw; row += 32) {
+                    cplx a = V[row + L * k], bq = V[row + L * (k + 1)];
+                    V[row + L * k] = cadd(cscale(a, c), cmul(csn, bq));
+                    V[row + L * (k + 1)] = csub(cscale(bq, c), cmul(sn, a));
+                }
+                __syncwarp();
+                if (lane == 0) { T[k + L * k] = t22; T[(k + 1) + L * (k + 1)] = t11; }
+                __syncwarp();
+            }
+            ++ilst;
+        }
+    }
+    if (ns == 0) s = mkc(0.0, 0.0);
+    for (int j = lane; j < ns; j += 32) shifts[j] = T[j + L * j];
+    const bool sz = (s.x == 0.0 && s.y == 0.0);
+    const int nd = nw - ns;
+    if (lane == 0) out[0] = (nd > 0 || sz) ? 1 : 0;
+    __syncwarp();
+    if (!(nd > 0 || sz)) return ns;
+    if (ns > 1 && !sz) {
+        // ---- reflect the spike w = s * conj(V[0, 0:ns]) to beta * e1 ----
+        double part = 0.0;
+        for (int j = lane; j < ns; j += 32) {
+            cplx w = cmul(s, cconj(V[0 + L * j]));
+            vbuf[j] = w;
+            if (j > 0) part += cabs2(w);
+        }
+        const double xnorm2 = warp_sum(part);
+        __syncwarp();
+        const cplx alpha = vbuf[0];
+        if (!(xnorm2 == 0.0 && alpha.y == 0.0)) {
+            const double beta = -copysign(sqrt(cabs2(alpha) + xnorm2), alpha.x);
+            const cplx tau = mkc((beta - alpha.x) / beta, -alpha.y / beta), ctau = cconj(tau);
+            const cplx scale = cdiv(mkc(1.0, 0.0), mkc(alpha.x - beta, alpha.y));
+            __syncwarp();
+            for (int j = lane; j < ns; j += 32) vbuf[j] = (j == 0) ? mkc(1.0, 0.0) : cmul(vbuf[j], scale);
+            __syncwarp();
+            for (int col = lane; col < nw; col += 32) {           // T[0:ns, :] <- P^H T
+                cplx d = mkc(0.0, 0.0);
+                for (int j = 0; j < ns; ++j) d = cfmac(vbuf[j], T[j + L * col], d);
+                const cplx f = cmul(ctau, d);
+                for (int j = 0; j < ns; ++j) T[j + L * col] = csub(T[j + L * col], cmul(f, vbuf[j]));
+            }
+            __syncwarp();
+            for (int row = lane; row < ns; row += 32) {           // T[0:ns, 0:ns] <- T P
+                cplx y = mkc(0.0, 0.0);
+                for (int j = 0; j < ns; ++j) y = cfma(T[row + L * j], vbuf[j], y);
+                const cplx f = cmul(tau, y);
+                for (int j = 0; j < ns; ++j) T[row + L * j] = csub(T[row + L * j], cmul(f, cconj(vbuf[j])));
+            }
+            for (int row = lane; row < nw; row += 32) {           // V[:, 0:ns] <- V P
+                cplx y = mkc(0.0, 0.0);
+                for (int j = 0; j < ns; ++j) y = cfma(V[row + L * j], vbuf[j], y);
+                const cplx f = cmul(tau, y);
+                for (int j = 0; j < ns; ++j) V[row + L * j] = csub(V[row + L * j], cmul(f, cconj(vbuf[j])));
+            }
+            __syncwarp();
+        }
+        // ---- restore Hessenberg form of T[0:ns, 0:ns] (Householder), carrying T[0:ns, ns:nw] and V[:, 0:ns] along ----
+        for (int k = 0; k + 2 < ns; ++k) {
+            const int len = ns - k - 1;
+            double pp = 0.0;
+            for (int i = 1 + lane; i < len; i += 32) pp += cabs2(T[(k + 1 + i) + L * k]);
+            const double xn2 = warp_sum(pp);
+            const cplx al = T[(k + 1) + L * k];
+            if (xn2 == 0.0 && al.y == 0.0) continue;
+            const double beta = -copysign(sqrt(cabs2(al) + xn2), al.x);
+            const cplx tau = mkc((beta - al.x) / beta, -al.y / beta), ctau = cconj(tau);
+            const cplx scale = cdiv(mkc(1.0, 0.0), mkc(al.x - beta, al.y));
+            __syncwarp();
+            for (int i = lane; i < len; i += 32) {
+                if (i == 0) { vbuf[0] = mkc(1.0, 0.0); T[(k + 1) + L * k] = mkc(beta, 0.0); }
+                else { vbuf[i] = cmul(T[(k + 1 + i) + L * k], scale); T[(k + 1 + i) + L * k] = mkc(0.0, 0.0); }
+            }
+            __syncwarp();
+            for (int col = k + 1 + lane; col < nw; col += 32) {   // left: rows k+1..ns-1
+                cplx d = mkc(0.0, 0.0);
+                for (int i = 0; i < len; ++i) d = cfmac(vbuf[i], T[(k + 1 + i) + L * col], d);
+                const cplx f = cmul(ctau, d);
+                for (int i = 0; i < len; ++i) T[(k + 1 + i) + L * col] = csub(T[(k + 1 + i) + L * col], cmul(f, vbuf[i]));
+            }
+            __syncwarp();
+            for (int row = lane; row < ns; row += 32) {           // right: cols k+1..ns-1 of T[0:ns, :]
+                cplx y = mkc(0.0, 0.0);
+                for (int i = 0; i < len; ++i) y = cfma(T[row + L * (k + 1 + i)], vbuf[i], y);
+                const cplx f = cmul(tau, y);
+                for (int i = 0; i < len; ++i) T[row + L * (k + 1 + i)] = csub(T[row + L * (k + 1 + i)], cmul(f, cconj(vbuf[i])));
+            }
+            for (int row = lane; row < nw; row += 32) {           // right on V
+                cplx y = mkc(0.0, 0.0);
+                for (int i = 0; i < len; ++i) y = cfma(V[row + L * (k + 1 + i)], vbuf[i], y);
+                const cplx f = cmul(tau, y);
+                for (int i = 0; i < len; ++i) V[row + L * (k + 1 + i)] = csub(V[row + L * (k + 1 + i)], cmul(f, cconj(vbuf[i])));
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) *newsub = cmul(s, cconj(V[0]));
+    __syncwarp();
+    return ns;
+}
+
+// ---------------------------------------------------------------------------------------------
 // apply the window transform Ww (64x64 in smem, identity-padded beyond ww) to the off-window strips:
 //   H[ws:we, we:n] <- Ww^H H[ws:we, we:n];  H[0:ws, ws:we] <- H[0:ws, ws:we] Ww;  Z[:, ws:we] <- Z[:, ws:we] Ww
 // all E_THREADS threads participate; tiles: 2 x E_TILE double buffer
@@ -579,37 +724,57 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
         }
         ++its;
         if (its > 60) { failed = true; break; }
-        // ---- shifts: eigenvalues of the trailing E_NB x E_NB block ----
-        if (its % 6 == 0) {
-            if (tid < E_NB) {
-                cplx d = Hb[(ihi - tid) + (long long)ld * (ihi - tid)];
-                cplx sub = Hb[(ihi - tid) + (long long)ld * (ihi - tid - 1)];
-                shifts[tid] = mkc(d.x + 0.75 * cabs_(sub), d.y);
-            }
-            __syncthreads();
-        } else {
-            for (int idx = tid; idx < E_NB * E_NB; idx += E_THREADS) {
-                int r = idx % E_NB, c = idx / E_NB;
-                cplx hv = Hb[(ihi - E_NB + 1 + r) + (long long)ld * (ihi - E_NB + 1 + c)];
-                if (r > c + 1) hv = mkc(0.0, 0.0);
-                Hs[r + E_LDS * c] = hv;
+        // ---- aggressive early deflation on the trailing E_NW x E_NW window; its undeflated eigenvalues are the shifts ----
+        int nbu = E_NB;
+        {
+            const int nw = E_NW;                      // size > E_W >= E_NW
+            const int kwtop = ihi - nw + 1;
+            const cplx spike = Hb[kwtop + (long long)ld * (kwtop - 1)];
+            for (int idx = tid; idx < E_W * E_W; idx += E_THREADS) {
+                int r = idx & 63, c = idx >> 6;
+                cplx hv = mkc(0.0, 0.0);
+                if (r < nw && c < nw && r <= c + 1) hv = Hb[(kwtop + r) + (long long)ld * (kwtop + c)];
+                Hw[r + E_LDW * c] = hv;
+                Ww[r + E_LDW * c] = mkc(r == c ? 1.0 : 0.0, 0.0);
             }
             __syncthreads();
             if (warp == 0) {
-                int r = warp_small_hqr(Hs, E_LDS, nullptr, 0, E_NB, 0);
+                int r = warp_aed(Hw, Ww, nw, spike, shifts, Hs, iscr + 33, Hs + 64);
                 if (lane == 0) iscr[32] = r;
-                __syncwarp();
-                if (lane < E_NB) shifts[lane] = Hs[lane + E_LDS * lane];
             }
             __syncthreads();
-            if (iscr[32] < 0) { failed = true; break; }
+            const int ns = iscr[32];
+            if (ns < 0) { failed = true; break; }
+            const int nd = nw - ns;
+            if (iscr[33]) {
+                for (int idx = tid; idx < nw * nw; idx += E_THREADS) {
+                    int r = idx % nw, c = idx / nw;
+                    Hb[(kwtop + r) + (long long)ld * (kwtop + c)] = (r <= c + 1) ? Hw[r + E_LDW * c] : mkc(0.0, 0.0);
+                }
+                if (tid == 0) Hb[kwtop + (long long)ld * (kwtop - 1)] = Hs[64];
+                apply_window_transform(Hb, Zb, ld, n, kwtop, ihi + 1, Ww, tiles, iscr + 40);
+            }
+            PROF(5);
+            if (nd > 0) { ihi -= nd; its = 0; }
+            if (nd * 100 > 14 * nw || ihi - ilo + 1 <= E_W) continue;     // good deflation: look again before sweeping
+            if (ns < 2 || (its > 0 && its % 6 == 0)) {
+                __syncthreads();
+                if (tid < E_NB) {
+                    cplx d = Hb[(ihi - tid) + (long long)ld * (ihi - tid)];
+                    cplx sub = Hb[(ihi - tid) + (long long)ld * (ihi - tid - 1)];
+                    shifts[tid] = mkc(d.x + 0.75 * cabs_(sub), d.y);
+                }
+                __syncthreads();
+            } else {
+                nbu = min(ns, E_NB);
+            }
         }
         // ---- one multishift sweep over [ilo, ihi] ----
         PROF(0);
         ++nsweeps;
         int tstep = 0;
         while (true) {
-            const int p_last = ilo - 1 - 2 * (E_NB - 1) + tstep;
+            const int p_last = ilo - 1 - 2 * (nbu - 1) + tstep;
             if (p_last > ihi - 2) break;
             const int p_top = max(ilo - 1, p_last);
             const int p0 = ilo - 1 + tstep;
@@ -629,7 +794,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             PROF(1);
             for (int step = 0; step < T; ++step) {
                 const int p = ilo - 1 - 2 * warp + tstep + step;     // this warp's bulge
-                const bool active = (p >= ilo - 1) && (p <= ihi - 2);
+                const bool active = (warp < nbu) && (p >= ilo - 1) && (p <= ihi - 2);
                 double c = 1.0; cplx s = mkc(0.0, 0.0);
                 if (active) {
                     cplx x, y;

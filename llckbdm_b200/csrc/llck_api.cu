@@ -466,8 +466,15 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             CK(cudaStreamSynchronize(st));
             double tot[6] = {0, 0, 0, 0, 0, 0};
             for (int b = 0; b < batch; ++b) for (int i = 0; i < 6; ++i) tot[i] += (double)hp[6 * b + i] / batch;
-            fprintf(stderr, "[llck] hqr phase Mcycles/member: scan+shifts=%.1f load=%.1f chase=%.1f store=%.1f strips=%.1f small=%.1f\n",
+            fprintf(stderr, "[llck] hqr phase Mcycles/member: scan+shifts=%.1f load=%.1f chase=%.1f store=%.1f strips=%.1f aed+small=%.1f\n",
                     tot[0] / 1e6, tot[1] / 1e6, tot[2] / 1e6, tot[3] / 1e6, tot[4] / 1e6, tot[5] / 1e6);
+            double mn = 1e300, mx = 0, mxa = 0, mxs = 0; int imx = 0;
+            for (int b = 0; b < batch; ++b) {
+                double t = 0; for (int i = 0; i < 6; ++i) t += (double)hp[6 * b + i];
+                if (t < mn) mn = t;
+                if (t > mx) { mx = t; imx = b; mxa = (double)hp[6 * b + 5]; mxs = (double)hp[6 * b + 4]; }
+            }
+            fprintf(stderr, "[llck] hqr per-member total Mcycles: min=%.1f max=%.1f (member %d: aed+small=%.1f strips=%.1f)\n", mn / 1e6, mx / 1e6, imx, mxa / 1e6, mxs / 1e6);
             free(hp); cudaFree(d_prof);
 
         }
