@@ -88,6 +88,11 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
 int llck_zgemm(int32_t amode, const void* A, int32_t lda, const void* B, int32_t ldb, void* C, int32_t ldc,
                int32_t M, int32_t N, int32_t K, const void* sig, int32_t shift, void* stream);
 
+/* Stage-level entry (tests): blocked Householder bidiagonalisation A = Q B P^H of one m x m matrix (column-major, ld).
+ * A [dev] is overwritten by the reflectors; d_out[m], e_out[m-1] [dev] = the REAL diagonal / superdiagonal of B;
+ * Q, P [dev] ld x m complex.  Allocates its own scratch (test helper, not part of the hot path). */
+int llck_bidiag_test(void* A, int32_t m, int32_t ld, double* d_out, double* e_out, void* Q, void* P, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

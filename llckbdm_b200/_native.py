@@ -17,6 +17,7 @@ SYMBOLS = (
     "llck_debug_offset",
     "llck_kbdm_batched",
     "llck_zgemm",
+    "llck_bidiag_test",
 )
 
 FLAG_DEBUG_KEEP = 1
@@ -67,6 +68,8 @@ def load():
     ]
     lib.llck_zgemm.restype = c_int
     lib.llck_zgemm.argtypes = [c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
+    lib.llck_bidiag_test.restype = c_int
+    lib.llck_bidiag_test.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
     _lib = lib
     return lib
 
