@@ -32,13 +32,18 @@ __global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, lon
     cplx* xrow = vrow + BD_NB;                             // X[c, :i]
     double* red = reinterpret_cast<double*>(xrow + BD_NB + 8);
     const int b = blockIdx.x, m = mv[b];
-    if (k0 >= m) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     cplx* Ab = A + (long long)b * stride;
     cplx* Vb = Vp + (long long)b * pstride;
     cplx* Yb = Yp + (long long)b * pstride;
     cplx* Xb = Xp + (long long)b * pstride;
     cplx* Ub = Up + (long long)b * pstride;
+    if (k0 >= m) {                                         // member already finished: neutral panel for the batched updates
+        for (int idx = tid; idx < ld * BD_NB; idx += E_THREADS) {
+            Vb[idx] = mkc(0.0, 0.0); Yb[idx] = mkc(0.0, 0.0); Xb[idx] = mkc(0.0, 0.0); Ub[idx] = mkc(0.0, 0.0);
+        }
+        return;
+    }
     double* db = dws + (long long)b * ld;
     double* eb = ews + (long long)b * ld;
     const long long tpan = (long long)(k0 / BD_NB) * BD_NB * BD_NB;
@@ -207,10 +212,13 @@ __global__ void __launch_bounds__(E_THREADS, 1) bidiag_qpanel_kernel(const cplx*
     __shared__ cplx Tsm[BD_NB * BD_NB];
     const int b = blockIdx.x, m = mv[b];
     const int tid = threadIdx.x;
-    if (k0 >= m) return;
     const cplx* Ab = A + (long long)b * stride;
     cplx* Vb = Vp + (long long)b * pstride;
     cplx* VTb = VTp + (long long)b * pstride;
+    if (k0 >= m) {
+        for (int idx = tid; idx < ld * BD_NB; idx += E_THREADS) { Vb[idx] = mkc(0.0, 0.0); VTb[idx] = mkc(0.0, 0.0); }
+        return;
+    }
     const cplx* Tb = Tws + (long long)b * tstride + (long long)(k0 / BD_NB) * BD_NB * BD_NB;
     for (int idx = tid; idx < BD_NB * BD_NB; idx += E_THREADS) Tsm[idx] = Tb[idx];
     __syncthreads();

@@ -140,11 +140,14 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
     double* red = reinterpret_cast<double*>(vrow + HB_NB);
     const int b = blockIdx.x, n = lv[b];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (k0 + 2 >= n) return;                               // nothing left to reduce for this member
     cplx* Hb = H + (long long)b * stride;
     cplx* Vb = Vp + (long long)b * pstride;
     cplx* Yb = Yp + (long long)b * pstride;
     cplx* VTb = VTp + (long long)b * pstride;
+    if (k0 + 2 >= n) {                                     // nothing left to reduce for this member: neutral panel
+        for (int idx = tid; idx < ld * HB_NB; idx += E_THREADS) { Vb[idx] = mkc(0.0, 0.0); Yb[idx] = mkc(0.0, 0.0); VTb[idx] = mkc(0.0, 0.0); }
+        return;
+    }
     cplx* Tb = Tws + (long long)b * tstride + (long long)(k0 / HB_NB) * HB_NB * HB_NB;
 
     for (int idx = tid; idx < HB_NB * HB_NB; idx += E_THREADS) Tsm[idx] = mkc(0.0, 0.0);
@@ -273,10 +276,13 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_qpanel_kernel(const cplx* H
     __shared__ cplx Tsm[HB_NB * HB_NB];
     const int b = blockIdx.x, n = lv[b];
     const int tid = threadIdx.x;
-    if (k0 + 2 >= n) return;
     const cplx* Hb = H + (long long)b * stride;
     cplx* Vb = Vp + (long long)b * pstride;
     cplx* VTb = VTp + (long long)b * pstride;
+    if (k0 + 2 >= n) {
+        for (int idx = tid; idx < ld * HB_NB; idx += E_THREADS) { Vb[idx] = mkc(0.0, 0.0); VTb[idx] = mkc(0.0, 0.0); }
+        return;
+    }
     const cplx* Tb = Tws + (long long)b * tstride + (long long)(k0 / HB_NB) * HB_NB * HB_NB;
     for (int idx = tid; idx < HB_NB * HB_NB; idx += E_THREADS) Tsm[idx] = Tb[idx];
     __syncthreads();

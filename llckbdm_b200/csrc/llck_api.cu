@@ -13,6 +13,7 @@
 #include "svd.cuh"
 #include "eig.cuh"
 #include "bidiag.cuh"
+#include "svd_real.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -60,7 +61,7 @@ __global__ void mark_unconverged_kernel(const int* done, int* status, int batch)
 
 // ---- workspace layout -----------------------------------------------------------------------------
 struct WsLayout {
-    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, jws, gws, offws, skip, mats, total;
+    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, mats, total;
     int nmats;
 };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -83,6 +84,10 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
     L.vtp = o; o = al256(o + pan);
     L.wp = o; o = al256(o + pan);
     L.tws = o; o = al256(o + pan);
+    L.pan6 = o; o = al256(o + pan);
+    L.pan7 = o; o = al256(o + pan);
+    L.dws = o; o = al256(o + sizeof(double) * (size_t)batch * ld);
+    L.ews = o; o = al256(o + sizeof(double) * (size_t)batch * ld);
     const int pairs_max = ((ld / J_B) + 1) / 2 + 1;
     L.jws = o; o = al256(o + sizeof(cplx) * (size_t)batch * pairs_max * 4096);
     L.skip = o; o = al256(o + sizeof(int) * (size_t)batch * pairs_max);
@@ -288,6 +293,17 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     CK(cudaMemsetAsync(d_hqrs, 0, sizeof(int) * batch, st));
 
     // ---- SVD of U^{p-1} ----
+    const char* smode = getenv("LLCK_SVD");
+    const bool svd_bidiag = !(smode && smode[0] == 'j');      // default: bidiagonalise + real Jacobi; LLCK_SVD=j: complex Jacobi on U directly
+    int sweeps_run = 0;
+    int launches = 1;   // svd_init
+    int jac_rounds = 0;
+    double upd_us = 0.0; int upd_launches = 0;
+    const bool verbose = getenv("LLCK_VERBOSE") != nullptr;
+    double conv2 = 1e-12;   // a member is converged when no pair exceeded 1e-6 (scaled) during a sweep: the sweep leaves <= ~1e-12
+    if (const char* ev = getenv("LLCK_JACOBI_CONV")) { double c = atof(ev); conv2 = c * c; }
+    int inner_sweeps = 1;
+    if (const char* ev = getenv("LLCK_JACOBI_INNER")) inner_sweeps = atoi(ev);
     TICK();   // 0
     {
         dim3 grid(256, batch);
@@ -295,19 +311,116 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         CK(cudaGetLastError());
     }
     TICK();   // 1: init done
+    if (svd_bidiag) {
+        // (1) U^{p-1} = Q B P^H, B real upper bidiagonal
+        cplx* bQ = dbg ? mat(9) : mat(1);
+        cplx* bPm = dbg ? mat(11) : mat(4);
+        cplx* bReal = dbg ? mat(12) : mat(5);
+        cplx* bLpre = dbg ? mat(6) : mat(2);
+        cplx* bRpre = dbg ? mat(7) : mat(0);
+        const long long pstride = (long long)ld * BD_NB;
+        double* dws = (double*)(ws + L.dws); double* ews = (double*)(ws + L.ews);
+        {
+            int rc = bidiag_driver(bX, bQ, bPm, stride, ld, d_mv, mmax, batch, (cplx*)(ws + L.vp), (cplx*)(ws + L.yp), (cplx*)(ws + L.vtp),
+                                   (cplx*)(ws + L.pan6), (cplx*)(ws + L.wp), pstride, (cplx*)(ws + L.tws), (cplx*)(ws + L.pan7), dws, ews, st);
+            if (rc) return rc;
+        }
+        // (2) SVD of B by real block one-sided Jacobi
+        double* Xr = (double*)bReal;
+        double* Vr = Xr + (long long)ld * ld;
+        const long long rstride = 2 * stride;       // doubles per member
+        {
+            dim3 grid(256, batch);
+            rsvd_init_kernel<<<grid, 256, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_nbv, dws, ews);
+            CK(cudaGetLastError());
+        }
+        CK(cudaFuncSetAttribute(rjacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_GRAM_SMEM));
+        CK(cudaFuncSetAttribute(rjacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RJE_SMEM));
+        CK(cudaFuncSetAttribute(rjacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_UPD_SMEM));
+        RJacobiParams rp;
+        rp.X = Xr; rp.V = Vr; rp.stride = rstride; rp.ld = ld; rp.mv = d_mv; rp.nbv = d_nbv; rp.sweep_off = d_swoff; rp.done = d_done;
+        rp.tol2 = 1e-28; rp.inner_sweeps = inner_sweeps;
+        rp.Jws = (double*)(ws + L.jws); rp.Gws = (double*)(ws + L.gws); rp.offws = (double*)(ws + L.offws); rp.skip = (int*)(ws + L.skip);
+        rp.pairs_max = ((ld / J_B) + 1) / 2 + 1;
+        cudaEvent_t uev[128];
+        if (timing) for (int i = 0; i < 128; ++i) CK(cudaEventCreate(&uev[i]));
+        int h_active = batch;
+        for (int sweep = 0; sweep < 30 && h_active > 0; ++sweep) {
+            for (int r = 0; r < nbmax - 1; ++r) {
+                rp.round = r;
+                dim3 gA(nbmax / 2, batch), gA2(nbmax / 2, batch, 2);
+                rjacobi_gram_kernel<<<gA, 256, RJ_GRAM_SMEM, st>>>(rp);
+                rjacobi_eig_kernel<<<gA, RJE_THREADS, RJE_SMEM, st>>>(rp);
+                if (timing && r < 64) CK(cudaEventRecord(uev[2 * r], st));
+                rjacobi_update_kernel<<<gA2, 256, RJ_UPD_SMEM, st>>>(rp);
+                if (timing && r < 64) CK(cudaEventRecord(uev[2 * r + 1], st));
+            }
+            launches += 3 * (nbmax - 1) + 1;
+            CK(cudaGetLastError());
+            if (verbose) {
+                unsigned long long* h = (unsigned long long*)malloc(sizeof(unsigned long long) * batch);
+                CK(cudaMemcpyAsync(h, d_swoff, sizeof(unsigned long long) * batch, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                double mx = 0.0, mn = 1e300;
+                for (int b = 0; b < batch; ++b) { double v; memcpy(&v, &h[b], 8); v = sqrt(v); if (v > mx) mx = v; if (v < mn) mn = v; }
+                fprintf(stderr, "[llck] real jacobi sweep %d: active=%d  max off (pre-rotation) over members: max=%.3e min=%.3e\n", sweep, h_active, mx, mn);
+                free(h);
+            }
+            CK(cudaMemsetAsync(d_nact, 0, sizeof(int), st));
+            jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, d_nact, batch, conv2);
+            CK(cudaMemcpyAsync(&h_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ++sweeps_run;
+            jac_rounds += nbmax - 1;
+            if (timing) {
+                for (int r = 0; r < nbmax - 1 && r < 64; ++r) {
+                    float ms = 0.f;
+                    CK(cudaEventElapsedTime(&ms, uev[2 * r], uev[2 * r + 1]));
+                    upd_us += 1000.0 * ms; ++upd_launches;
+                }
+            }
+        }
+        if (timing) for (int i = 0; i < 128; ++i) cudaEventDestroy(uev[i]);
+        TICK();   // 2: jacobi done
+        if (h_active > 0) {
+            mark_unconverged_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_done, status, batch);
+            CK(cudaGetLastError());
+        }
+        // (3) singular values, truncation/scaling, back-multiplication by Q and P
+        int npow2 = 64;
+        while (npow2 < ld) npow2 <<= 1;
+        rsvd_finalize_kernel<<<batch, 256, npow2 * 12, st>>>(Xr, rstride, ld, d_mv, d_nbv, sing_vals, sv_stride, d_perm, npow2);
+        CK(cudaGetLastError());
+        {
+            dim3 grid(lmax, batch);
+            rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 0);
+            CK(cudaGetLastError());
+        }
+        GemmParams g = gemm_params_zero();          // Lt = Q * Lpre
+        g.A = bQ; g.strideA = stride; g.lda = ld; g.B = bLpre; g.strideB = stride; g.ldb = ld; g.C = bLt; g.strideC = stride; g.ldc = ld;
+        g.Mv = d_mv; g.Nv = d_lv; g.Kv = d_mv;
+        CK(zgemm_batched(A_NORMAL, g, mmax, lmax, mmax, batch, st));
+        g.A = bPm; g.B = bRpre; g.C = bRs;            // Rs = P * Rpre
+        CK(zgemm_batched(A_NORMAL, g, mmax, lmax, mmax, batch, st));
+        if (dbg) {      // X_dbg = Q * X[:,perm] (= L Sigma), V_dbg = P * V[:,perm] (= R) for the stage checker
+            CK(cudaMemsetAsync(mat(0), 0, sizeof(cplx) * batch * stride, st));
+            CK(cudaMemsetAsync(mat(1), 0, sizeof(cplx) * batch * stride, st));
+            dim3 grid(mmax, batch);
+            rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 1);
+            CK(cudaGetLastError());
+            g.A = bQ; g.B = bLpre; g.C = mat(0); g.Nv = d_mv;
+            CK(zgemm_batched(A_NORMAL, g, mmax, mmax, mmax, batch, st));
+            g.A = bPm; g.B = bRpre; g.C = mat(1);
+            CK(zgemm_batched(A_NORMAL, g, mmax, mmax, mmax, batch, st));
+        }
+    } else {
     CK(cudaFuncSetAttribute(jacobi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, J_SMEM_BYTES));
     JacobiParams jp;
     jp.X = bX; jp.V = bV; jp.stride = stride; jp.ld = ld; jp.mv = d_mv; jp.nbv = d_nbv;
     jp.sweep_off = d_swoff; jp.done = d_done; jp.tol2 = 1e-28;
-    jp.inner_sweeps = 1;
-    if (const char* ev = getenv("LLCK_JACOBI_INNER")) jp.inner_sweeps = atoi(ev);
-    int sweeps_run = 0;
-    int launches = 1;   // svd_init
+    jp.inner_sweeps = inner_sweeps;
     const int max_sweeps = 30;
     int h_active = batch;
-    const bool verbose = getenv("LLCK_VERBOSE") != nullptr;
-    double conv2 = 1e-12;   // a member is converged when no pair exceeded 1e-6 (scaled) during a sweep: the sweep leaves <= ~1e-12
-    if (const char* ev = getenv("LLCK_JACOBI_CONV")) { double c = atof(ev); conv2 = c * c; }
     const char* jmode = getenv("LLCK_JACOBI");
     const bool fused = (jmode && jmode[0] == 'f');
     JacobiSplitParams sp;
@@ -319,7 +432,6 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         CK(cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JS_UPD_SMEM));
     }
     cudaEvent_t uev[128];
-    double upd_us = 0.0; int upd_launches = 0;
     if (timing) for (int i = 0; i < 128; ++i) CK(cudaEventCreate(&uev[i]));
     cudaStream_t st2 = nullptr;
     cudaEvent_t ev2 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
@@ -407,6 +519,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         CK(cudaMemcpyAsync(&h_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         ++sweeps_run;
+        jac_rounds += nbmax - 1;
         if (timing && three) {
             for (int r = 0; r < nbmax - 1 && r < 64; ++r) {
                 float ms = 0.f;
@@ -432,6 +545,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         dim3 grid(lmax, batch);
         svd_gather_kernel<<<grid, 128, 0, st>>>(bX, bV, stride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bRs, bLt, status);
         CK(cudaGetLastError());
+    }
     }
     TICK();   // 3: finalize+gather done
     // ---- reduced operator ----
@@ -624,7 +738,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         }
         info[0] = sweeps_run; info[1] = h_maxs; info[2] = ld; info[3] = nbmax;
         info[13] = launches + 2 /*finalize, gather*/ + 5 /*gemms*/ + 3 /*hessenberg, hqr, trevc*/ + 1 /*epilogue*/;
-        info[14] = sweeps_run * (nbmax - 1);   // Jacobi rounds (one gram + eig + update launch each)
+        info[14] = jac_rounds;   // Jacobi rounds (one gram + eig + update launch each)
         info[15] = (upd_launches > 0) ? (int32_t)(upd_us / upd_launches) : 0;   // avg jacobi_update_kernel duration (us), timing mode
     }
     CK(cudaStreamSynchronize(st));
