@@ -9,7 +9,7 @@ Hankel dimension m = 1024, l = m, p = 1, q = 0  (BASELINE.json: "KBDM solves/sec
   value     whole-job solves/s with the FIDs already resident in HBM (CUDA events, max over ranks)
   e2e       the same through the public host API (ensemble.solve_ensemble: host FIDs in, host line lists out;
             H2D + D2H inside the timed region)
-  roofline  dominant kernel (jacobi_update_kernel): algorithmic FP64 flops per launch / measured launch time
+  roofline  dominant kernel (hqr_kernel): algorithmic FP64 flops per launch / measured launch time
             vs the FP64 tensor (DMMA) peak measured on this pool (profiles/fp64_peak_r01.json -- MEASURED_PEAKS.json
             carries no FP64 figure)
   cpu_baseline  the numpy/scipy restatement of the reference (oracle/, kind "port") timed on the host cores
@@ -241,16 +241,22 @@ def run_native(args):
     e2e_val = world * batch * args.steps / (float(t.item()) * 1e-3)
     bad += int((res.status != 0).sum())
 
-    # ---- roofline of the dominant kernel (block-Jacobi SVD step) ----
+    # ---- roofline of the dominant kernel ----
+    # By device time the top kernel is hqr_kernel (small-bulge multishift QR + AED, one launch per step, ~24 % of the step).
+    # Algorithmic flops (SURVEY.md §8d, K5 = 108 l^3 for the whole eig): QR iterations with Schur vectors = 80 l^3 real flops per
+    # member (108 l^3 minus Hessenberg 13.3 l^3, Q formation 5.3 l^3, eigenvector back-substitution + back-transform 9.3 l^3).
+    # Duration = CUDA events around the launch inside the timed region (stage timer info[9]).
     peak, peak_src = fp64_peak_tflops()
+    hqr_s = (stage_us[5] * 1e-6) / args.steps
+    flops_per_launch = 80.0 * float(m) ** 3 * batch
+    achieved = flops_per_launch / hqr_s / 1e12
+    # secondary: the Jacobi update kernel (real DMMA GEMM of the X and V panels of every pair of a round), timed per launch
     nb = 2 * ((m + 63) // 64)
-    # dominant kernel: jacobi_update_kernel (Xp <- Xp J and Vp <- Vp J for every pair of a round): 2 x 32 b^2 m flop per pair,
-    # duration = CUDA events around every launch inside the timed region (info[15], averaged over the steps)
-    flops_per_launch = 64.0 * 32 * 32 * m * (nb // 2) * batch
-    jac_s_per_launch = float(np.mean(upd_us)) * 1e-6 if np.mean(upd_us) > 0 else (stage_us[1] * 1e-6) / max(jac_launches, 1)
-    achieved = flops_per_launch / jac_s_per_launch / 1e12
+    upd_flops = 2.0 * 2.0 * 32 * 32 * m * 2 * (nb // 2) * batch * 2 / 2          # 2 panels x (m x 64 x 64) real MACs x 2 flop
+    upd_flops = 2.0 * (m * 64.0 * 64.0) * 2 * (nb // 2) * batch
+    upd_s = float(np.mean(upd_us)) * 1e-6 if np.mean(upd_us) > 0 else None
     alg_flops = ensemble.flops_per_solve(m, m) * batch * args.steps
-    names = ["init", "jacobi_svd", "finalize_gather", "gemm_T1_Ured", "hessenberg", "hqr", "trevc", "gemm_P_B_W", "epilogue"]
+    names = ["init_bidiag", "jacobi_svd", "finalize_backmult", "gemm_T1_Ured", "hessenberg", "hqr", "trevc", "gemm_P_B_W", "epilogue"]
 
     out = {
         "metric": "kbdm_solves_per_sec_m1024", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
@@ -262,10 +268,14 @@ def run_native(args):
         "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "jacobi_update_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "tensor", "kernel": "hqr_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "launches": int(jac_launches), "avg_launch_ms": jac_s_per_launch * 1e3,
+                     "launches": int(args.steps), "avg_launch_ms": hqr_s * 1e3,
                      "algorithmic_flops_per_launch": flops_per_launch},
+        "roofline_secondary": {"bound": "tensor", "kernel": "rjacobi_update_kernel", "achieved": (upd_flops / upd_s / 1e12) if upd_s else None,
+                               "peak": peak, "unit": "TFLOP/s", "frac": (upd_flops / upd_s / 1e12 / peak) if upd_s else None,
+                               "launches": int(jac_launches), "avg_launch_ms": (upd_s * 1e3) if upd_s else None,
+                               "algorithmic_flops_per_launch": upd_flops},
         "fp64_roofline_whole_solve": {"algorithmic_tflops": alg_flops / (ms_total * 1e-3) / 1e12 / 1.0,
                                       "frac_of_peak_per_gpu": alg_flops / (ms_total * 1e-3) / 1e12 / peak,
                                       "flops_per_solve": ensemble.flops_per_solve(m, m)},

@@ -310,7 +310,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         svd_init_kernel<<<grid, 256, 0, st>>>(bX, bV, stride, ld, d_mv, d_nbv, (const cplx*)signals, d_soff, p - 1);
         CK(cudaGetLastError());
     }
-    TICK();   // 1: init done
+    if (!svd_bidiag) TICK();   // 1: init done
     if (svd_bidiag) {
         // (1) U^{p-1} = Q B P^H, B real upper bidiagonal
         cplx* bQ = dbg ? mat(9) : mat(1);
@@ -325,6 +325,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
                                    (cplx*)(ws + L.pan6), (cplx*)(ws + L.wp), pstride, (cplx*)(ws + L.tws), (cplx*)(ws + L.pan7), dws, ews, st);
             if (rc) return rc;
         }
+        TICK();   // 1: init + bidiagonalisation done
         // (2) SVD of B by real block one-sided Jacobi
         double* Xr = (double*)bReal;
         double* Vr = Xr + (long long)ld * ld;

@@ -12,7 +12,7 @@ flat, offs = ensemble.flatten_signals(sigs, batch)
 dev = torch.device("cuda:0")
 sig_dev = torch.from_numpy(flat.view(np.float64)).to(dev).view(torch.complex128)
 ws = None
-names = ["init", "jacobi", "final+gather", "T1+Ured", "hessenberg", "hqr", "trevc", "P+B+W", "epilogue"]
+names = ["init+bidiag", "jacobi", "final+gather", "T1+Ured", "hessenberg", "hqr", "trevc", "P+B+W", "epilogue"]
 for r in range(reps):
     torch.cuda.synchronize(); t0 = time.time()
     out = ensemble.solve_device(sig_dev, offs, [m] * batch, [m] * batch, 1, 0.0, 5e-4, flags=_native.FLAG_TIMING, workspace=ws)
