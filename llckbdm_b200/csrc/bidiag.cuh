@@ -110,20 +110,30 @@ __global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, lon
         if (tid == 0) TQ[i + BD_NB * i] = tau;
         if (c + 1 >= m) { __syncthreads(); continue; }
         // ---------- y = tau (A^H v - Y zv - U zx) on columns j > c   (pass 1 over the trailing matrix: column dots) ----------
-        for (int j = c + 1 + warp; j < m; j += E_NWARPS) {
-            const cplx* col = Ab + (long long)ld * j;
-            cplx d0 = mkc(0.0, 0.0), d1 = mkc(0.0, 0.0);
+        for (int j = c + 1 + 2 * warp; j < m; j += 2 * E_NWARPS) {          // two columns per warp, 4 independent loads each
+            const bool two = (j + 1 < m);
+            const cplx* col0 = Ab + (long long)ld * j;
+            const cplx* col1 = Ab + (long long)ld * (two ? j + 1 : j);
+            cplx a0 = mkc(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0, b0 = a0, b1 = a0, b2 = a0, b3 = a0;
             int r = c + lane;
-            for (; r + 32 < m; r += 64) { d0 = cfmac(col[r], vvec[r], d0); d1 = cfmac(col[r + 32], vvec[r + 32], d1); }
-            if (r < m) d0 = cfmac(col[r], vvec[r], d0);
-            cplx d = warp_sum(cadd(d0, d1));
-            if (lane == 0) {
+            for (; r + 96 < m; r += 128) {
+                const cplx v0 = vvec[r], v1 = vvec[r + 32], v2 = vvec[r + 64], v3 = vvec[r + 96];
+                const cplx x0 = col0[r], x1 = col0[r + 32], x2 = col0[r + 64], x3 = col0[r + 96];
+                const cplx y0 = col1[r], y1 = col1[r + 32], y2 = col1[r + 64], y3 = col1[r + 96];
+                a0 = cfmac(x0, v0, a0); a1 = cfmac(x1, v1, a1); a2 = cfmac(x2, v2, a2); a3 = cfmac(x3, v3, a3);
+                b0 = cfmac(y0, v0, b0); b1 = cfmac(y1, v1, b1); b2 = cfmac(y2, v2, b2); b3 = cfmac(y3, v3, b3);
+            }
+            for (; r < m; r += 32) { const cplx v0 = vvec[r]; a0 = cfmac(col0[r], v0, a0); b0 = cfmac(col1[r], v0, b0); }
+            cplx d0 = warp_sum(cadd(cadd(a0, a1), cadd(a2, a3)));
+            cplx d1 = warp_sum(cadd(cadd(b0, b1), cadd(b2, b3)));
+            if (lane < 2 && (lane == 0 || two)) {
+                const int jc = j + lane;
+                cplx d = lane ? d1 : d0;
                 for (int jj = 0; jj < i; ++jj) {
-                    d = csub(d, cmul(Yb[j + (long long)ld * jj], zv[jj]));
-                    d = csub(d, cmul(Ub[j + (long long)ld * jj], zx[jj]));
+                    d = csub(d, cmul(Yb[jc + (long long)ld * jj], zv[jj]));
+                    d = csub(d, cmul(Ub[jc + (long long)ld * jj], zx[jj]));
                 }
-                d = cmul(tau, d);
-                Yb[j + (long long)ld * i] = d;
+                Yb[jc + (long long)ld * i] = cmul(tau, d);
             }
         }
         if (tid <= i) vrow[tid] = Vb[c + (long long)ld * tid];

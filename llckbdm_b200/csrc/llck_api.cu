@@ -105,25 +105,27 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
 // A (in: matrices, out: reflectors + d/e), Q and P (out, ld x m each), panel buffers Vp/Yp/Xp/Up (ld x 32 each), Wp (32 x ld),
 // TQws/TPws ((ld/32) x 32 x 32 each), dws/ews (ld doubles each) -- all per member with the given strides.
 static int bidiag_driver(cplx* A, cplx* Q, cplx* P, long long stride, int ld, const int* d_mv, int mmax, int batch,
-                         cplx* Vp, cplx* Yp, cplx* Xp, cplx* Up, cplx* Wp, long long pstride, cplx* TQws, cplx* TPws,
+                         cplx* VX, cplx* YU, cplx* Wp, long long pstride, cplx* TQws, cplx* TPws,
                          double* dws, double* ews, cudaStream_t st) {
+    // VX = per member [V | X] (ld x 64), YU = per member [Y | U] (ld x 64): the panel's trailing update
+    //   A[e:, e:] -= V Y^H + X U^H  is ONE rank-64 GEMM  A[e:, e:] -= [V X] [Y U]^H
+    const long long pstride2 = 2 * pstride;
+    cplx* Vp = VX; cplx* Xp = VX + pstride; cplx* Yp = YU; cplx* Up = YU + pstride;
     size_t sm = (size_t)(2 * ld + 2 * BD_NB * BD_NB + 8 * BD_NB + 8) * 16 + 512;
     CK(cudaFuncSetAttribute(bidiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int k0_last = 0;
     for (int k0 = 0; k0 < mmax; k0 += BD_NB) {
         k0_last = k0;
-        bidiag_panel_kernel<<<batch, E_THREADS, sm, st>>>(A, stride, ld, d_mv, k0, Vp, Yp, Xp, Up, pstride, TQws, TPws, pstride, dws, ews);
+        bidiag_panel_kernel<<<batch, E_THREADS, sm, st>>>(A, stride, ld, d_mv, k0, Vp, Yp, Xp, Up, pstride2, TQws, TPws, pstride, dws, ews);
         CK(cudaGetLastError());
         const int e = k0 + BD_NB;
         if (e >= mmax) continue;
-        for (int which = 0; which < 2; ++which) {          // A[e:, e:] -= V Y^H ; A[e:, e:] -= X U^H
-            GemmParams g = gemm_params_zero();
-            g.A = (which ? Xp : Vp) + e; g.strideA = pstride; g.lda = ld;
-            g.B = (which ? Up : Yp) + e; g.strideB = pstride; g.ldb = ld;
-            g.C = A + e + (long long)ld * e; g.strideC = stride; g.ldc = ld;
-            g.Mv = d_mv; g.Mc = -e; g.Nv = d_mv; g.Nc = -e; g.Kc = BD_NB; g.accum = 1;
-            CK(zgemm_batched(A_NORMAL, g, mmax - e, mmax - e, BD_NB, batch, st, true));
-        }
+        GemmParams g = gemm_params_zero();
+        g.A = VX + e; g.strideA = pstride2; g.lda = ld;
+        g.B = YU + e; g.strideB = pstride2; g.ldb = ld;
+        g.C = A + e + (long long)ld * e; g.strideC = stride; g.ldc = ld;
+        g.Mv = d_mv; g.Mc = -e; g.Nv = d_mv; g.Nc = -e; g.Kc = 2 * BD_NB; g.accum = 1;
+        CK(zgemm_batched(A_NORMAL, g, mmax - e, mmax - e, 2 * BD_NB, batch, st, true));
     }
     dim3 gi(128, batch);
     set_identity_kernel<<<gi, 256, 0, st>>>(Q, stride, ld, d_mv);
@@ -135,16 +137,16 @@ static int bidiag_driver(cplx* A, cplx* Q, cplx* P, long long stride, int ld, co
         for (int k0 = k0_last; k0 >= 0; k0 -= BD_NB) {
             const int o = k0 + right;
             if (o >= mmax) continue;
-            bidiag_qpanel_kernel<<<batch, E_THREADS, 0, st>>>(A, stride, ld, d_mv, k0, right, Vp, Yp /*VTh*/, pstride, Tws, pstride);
+            bidiag_qpanel_kernel<<<batch, E_THREADS, 0, st>>>(A, stride, ld, d_mv, k0, right, Vp, Yp /*VTh*/, pstride2, Tws, pstride);
             CK(cudaGetLastError());
             GemmParams g = gemm_params_zero();          // W = (V T^H)[o:, :]^H * Acc[o:, o:]
-            g.A = Yp + o; g.strideA = pstride; g.lda = ld;
+            g.A = Yp + o; g.strideA = pstride2; g.lda = ld;
             g.B = Acc + o + (long long)ld * o; g.strideB = stride; g.ldb = ld;
             g.C = Wp; g.strideC = pstride; g.ldc = BD_NB;
             g.Mc = BD_NB; g.Nv = d_mv; g.Nc = -o; g.Kv = d_mv; g.Kc = -o;
             CK(zgemm_batched(A_CONJT, g, BD_NB, mmax - o, mmax - o, batch, st));
             g = gemm_params_zero();                     // Acc[o:, o:] -= V[o:, :] * W
-            g.A = Vp + o; g.strideA = pstride; g.lda = ld;
+            g.A = Vp + o; g.strideA = pstride2; g.lda = ld;
             g.B = Wp; g.strideB = pstride; g.ldb = BD_NB;
             g.C = Acc + o + (long long)ld * o; g.strideC = stride; g.ldc = ld;
             g.Mv = d_mv; g.Mc = -o; g.Nv = d_mv; g.Nc = -o; g.Kc = BD_NB; g.accum = 1;
@@ -202,13 +204,13 @@ int llck_bidiag_test(void* A, int32_t m, int32_t ld, double* d_out, double* e_ou
     unsigned char* w = nullptr;
     CK(cudaMalloc(&w, 7 * pan + 256));
     CK(cudaMemsetAsync(w, 0, 7 * pan + 256, st));
-    cplx* Vp = (cplx*)w; cplx* Yp = (cplx*)(w + pan); cplx* Xp = (cplx*)(w + 2 * pan); cplx* Up = (cplx*)(w + 3 * pan);
+    cplx* VX = (cplx*)w; cplx* YU = (cplx*)(w + 2 * pan);
     cplx* Wp = (cplx*)(w + 4 * pan); cplx* TQ = (cplx*)(w + 5 * pan); cplx* TP = (cplx*)(w + 6 * pan);
     int* d_m = (int*)(w + 7 * pan);
     CK(cudaMemcpyAsync(d_m, &m, sizeof(int), cudaMemcpyHostToDevice, st));
     double* dd = nullptr;
     CK(cudaMalloc(&dd, sizeof(double) * 2 * ld));
-    int rc = bidiag_driver((cplx*)A, (cplx*)Q, (cplx*)P, (long long)ld * ld, ld, d_m, m, 1, Vp, Yp, Xp, Up, Wp, (long long)ld * BD_NB, TQ, TP, dd, dd + ld, st);
+    int rc = bidiag_driver((cplx*)A, (cplx*)Q, (cplx*)P, (long long)ld * ld, ld, d_m, m, 1, VX, YU, Wp, (long long)ld * BD_NB, TQ, TP, dd, dd + ld, st);
     if (rc == 0) {
         cudaMemcpyAsync(d_out, dd, sizeof(double) * m, cudaMemcpyDeviceToDevice, st);
         cudaMemcpyAsync(e_out, dd + ld, sizeof(double) * (m > 1 ? m - 1 : 0), cudaMemcpyDeviceToDevice, st);
@@ -321,8 +323,9 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         const long long pstride = (long long)ld * BD_NB;
         double* dws = (double*)(ws + L.dws); double* ews = (double*)(ws + L.ews);
         {
-            int rc = bidiag_driver(bX, bQ, bPm, stride, ld, d_mv, mmax, batch, (cplx*)(ws + L.vp), (cplx*)(ws + L.yp), (cplx*)(ws + L.vtp),
-                                   (cplx*)(ws + L.pan6), (cplx*)(ws + L.wp), pstride, (cplx*)(ws + L.tws), (cplx*)(ws + L.pan7), dws, ews, st);
+            // [V|X] lives in the (vp, yp) pair of panel buffers, [Y|U] in (vtp, wp): both pairs are contiguous in the workspace
+            int rc = bidiag_driver(bX, bQ, bPm, stride, ld, d_mv, mmax, batch, (cplx*)(ws + L.vp), (cplx*)(ws + L.vtp),
+                                   (cplx*)(ws + L.pan6), pstride, (cplx*)(ws + L.tws), (cplx*)(ws + L.pan7), dws, ews, st);
             if (rc) return rc;
         }
         TICK();   // 1: init + bidiagonalisation done
