@@ -160,6 +160,18 @@ __device__ __forceinline__ void zmma_load_frags(cplx (&a)[MT], cplx (&b)[NT], co
 
 // 4 real DMMAs per complex tile product, issued as two passes over all tiles so that the two DMMAs that hit the same
 // accumulator pair are 2*MT*NT instructions apart (the dependent-issue latency of DMMA is long).
+// real B operand (imaginary parts known to be zero): two DMMAs per tile product instead of four
+template <int MT, int NT>
+__device__ __forceinline__ void zmma_compute_breal(double (&acc)[MT][NT][4], const cplx (&a)[MT], const cplx (&b)[NT]) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+            dmma(acc[i][j][2], acc[i][j][3], a[i].y, b[j].x);
+        }
+}
+
 template <int MT, int NT>
 __device__ __forceinline__ void zmma_compute(double (&acc)[MT][NT][4], const cplx (&a)[MT], const cplx (&b)[NT]) {
 #pragma unroll
@@ -180,7 +192,7 @@ __device__ __forceinline__ void zmma_compute(double (&acc)[MT][NT][4], const cpl
     }
 }
 
-template <int MT, int NT, bool CONJA, bool CONJB>
+template <int MT, int NT, bool CONJA, bool CONJB, bool BREAL = false>
 __device__ __forceinline__ void warp_zmma(double (&acc)[MT][NT][4], const cplx* __restrict__ A, int a_si, int a_sk,
                                           const cplx* __restrict__ B, int b_sk, int b_sj, int kcount) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -193,11 +205,11 @@ __device__ __forceinline__ void warp_zmma(double (&acc)[MT][NT][4], const cplx* 
     int k = 0;
     while (true) {
         if (k + 4 < kcount) zmma_load_frags<MT, NT, CONJA, CONJB>(a1, b1, ap, a_si, a_sk, bp, b_sk, b_sj, k + 4);
-        zmma_compute<MT, NT>(acc, a0, b0);
+        if (BREAL) zmma_compute_breal<MT, NT>(acc, a0, b0); else zmma_compute<MT, NT>(acc, a0, b0);
         k += 4;
         if (k >= kcount) break;
         if (k + 4 < kcount) zmma_load_frags<MT, NT, CONJA, CONJB>(a0, b0, ap, a_si, a_sk, bp, b_sk, b_sj, k + 4);
-        zmma_compute<MT, NT>(acc, a1, b1);
+        if (BREAL) zmma_compute_breal<MT, NT>(acc, a1, b1); else zmma_compute<MT, NT>(acc, a1, b1);
         k += 4;
         if (k >= kcount) break;
     }

@@ -22,6 +22,7 @@ struct GemmParams {
     int Mc, Nc, Kc;                                  // constants added to the per-member dims (dims = v[b] + c)
     int accum;                                       // 0: C = A*B ; 1: C -= A*B
     int Kcap;                                        // if > 0: K = min(K, Kcap)
+    int triB;                                        // B upper triangular: K is capped at the tile's last column + 1
     // Hankel source
     const cplx* sig; const long long* sig_off; int shift;
 };
@@ -29,7 +30,7 @@ struct GemmParams {
 static inline GemmParams gemm_params_zero() {
     GemmParams p;
     p.A = nullptr; p.strideA = 0; p.lda = 0; p.B = nullptr; p.strideB = 0; p.ldb = 0; p.C = nullptr; p.strideC = 0; p.ldc = 0;
-    p.Mv = p.Nv = p.Kv = nullptr; p.Mc = p.Nc = p.Kc = 0; p.accum = 0; p.Kcap = 0; p.sig = nullptr; p.sig_off = nullptr; p.shift = 0;
+    p.Mv = p.Nv = p.Kv = nullptr; p.Mc = p.Nc = p.Kc = 0; p.accum = 0; p.Kcap = 0; p.triB = 0; p.sig = nullptr; p.sig_off = nullptr; p.shift = 0;
     return p;
 }
 
@@ -44,7 +45,8 @@ static inline GemmParams gemm_params_zero() {
 #define G_SIG_MAX 4352  // max Hankel slice (complex) kept in smem: supports m up to 2048+
 
 // BCONJT: the B operand is stored N x K column-major and used as conj(B)^T (C -= Y * V^H)
-template <int AMODE, bool BCONJT>
+// BREAL : the B operand has zero imaginary parts (complex x real product: half the DMMAs)
+template <int AMODE, bool BCONJT, bool BREAL = false>
 __global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* smem = reinterpret_cast<cplx*>(smem_raw);
@@ -52,6 +54,7 @@ __global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
     const int M = (p.Mv ? p.Mv[b] : 0) + p.Mc, N = (p.Nv ? p.Nv[b] : 0) + p.Nc;
     int K = (p.Kv ? p.Kv[b] : 0) + p.Kc;
     if (p.Kcap > 0 && K > p.Kcap) K = p.Kcap;
+    if (p.triB && K > (int)blockIdx.y * G_BN + G_BN) K = (int)blockIdx.y * G_BN + G_BN;
     const int row0 = blockIdx.x * G_BM, col0 = blockIdx.y * G_BN;
     if (row0 >= M || col0 >= N || K <= 0) return;
 
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
         }
         __syncthreads();
         if (AMODE == A_NORMAL) {
-            warp_zmma<2, 4, false, BCONJT>(acc, As[buf] + 16 * wr, 1, G_LDA_N, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
+            warp_zmma<2, 4, false, BCONJT, BREAL>(acc, As[buf] + 16 * wr, 1, G_LDA_N, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
         } else if (AMODE == A_CONJT) {
             warp_zmma<2, 4, true, BCONJT>(acc, As[buf] + G_LDA_T * (16 * wr), G_LDA_T, 1, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
         } else {
@@ -183,19 +186,20 @@ static inline size_t zgemm_smem_bytes(int amode, int Kmax) {
 }
 
 // Launch: grid = (ceil(Mmax/64), ceil(Nmax/64), batch)
-template <int AMODE, bool BCONJT>
+template <int AMODE, bool BCONJT, bool BREAL = false>
 static inline cudaError_t zgemm_launch(const GemmParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(zgemm_batched_kernel<AMODE, BCONJT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(zgemm_batched_kernel<AMODE, BCONJT, BREAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    zgemm_batched_kernel<AMODE, BCONJT><<<grid, 256, smem, stream>>>(p);
+    zgemm_batched_kernel<AMODE, BCONJT, BREAL><<<grid, 256, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 static inline cudaError_t zgemm_batched(int amode, const GemmParams& p, int Mmax, int Nmax, int Kmax, int batch,
-                                        cudaStream_t stream, bool bconjt = false) {
+                                        cudaStream_t stream, bool bconjt = false, bool breal = false) {
     if (batch <= 0 || Mmax <= 0 || Nmax <= 0 || Kmax <= 0) return cudaSuccess;
     dim3 grid((Mmax + G_BM - 1) / G_BM, (Nmax + G_BN - 1) / G_BN, batch);
     size_t smem = zgemm_smem_bytes(amode, Kmax);
+    if (amode == A_NORMAL && breal) return zgemm_launch<A_NORMAL, false, true>(p, grid, smem, stream);
     if (amode == A_NORMAL) return bconjt ? zgemm_launch<A_NORMAL, true>(p, grid, smem, stream) : zgemm_launch<A_NORMAL, false>(p, grid, smem, stream);
     if (amode == A_CONJT) return zgemm_launch<A_CONJT, false>(p, grid, smem, stream);
     if (64 + Kmax + 32 > G_SIG_MAX) return cudaErrorInvalidValue;

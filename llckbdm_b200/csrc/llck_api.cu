@@ -403,9 +403,9 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         GemmParams g = gemm_params_zero();          // Lt = Q * Lpre
         g.A = bQ; g.strideA = stride; g.lda = ld; g.B = bLpre; g.strideB = stride; g.ldb = ld; g.C = bLt; g.strideC = stride; g.ldc = ld;
         g.Mv = d_mv; g.Nv = d_lv; g.Kv = d_mv;
-        CK(zgemm_batched(A_NORMAL, g, mmax, lmax, mmax, batch, st));
+        CK(zgemm_batched(A_NORMAL, g, mmax, lmax, mmax, batch, st, false, true));        // Lpre / Rpre are real
         g.A = bPm; g.B = bRpre; g.C = bRs;            // Rs = P * Rpre
-        CK(zgemm_batched(A_NORMAL, g, mmax, lmax, mmax, batch, st));
+        CK(zgemm_batched(A_NORMAL, g, mmax, lmax, mmax, batch, st, false, true));
         if (dbg) {      // X_dbg = Q * X[:,perm] (= L Sigma), V_dbg = P * V[:,perm] (= R) for the stage checker
             CK(cudaMemsetAsync(mat(0), 0, sizeof(cplx) * batch * stride, st));
             CK(cudaMemsetAsync(mat(1), 0, sizeof(cplx) * batch * stride, st));
@@ -710,8 +710,9 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     gp.A = bZ; gp.strideA = stride; gp.lda = ld;
     gp.B = bXev; gp.strideB = stride; gp.ldb = ld;
     gp.C = bP; gp.strideC = stride; gp.ldc = ld;
-    gp.Mv = d_lv; gp.Nv = d_lv; gp.Kv = d_lv;
+    gp.Mv = d_lv; gp.Nv = d_lv; gp.Kv = d_lv; gp.triB = 1;      // Xev is upper triangular
     CK(zgemm_batched(A_NORMAL, gp, lmax, lmax, lmax, batch, st));
+    gp.triB = 0;
     // B = Rs * P
     gp.A = bRs; gp.B = bP; gp.C = bB;
     gp.Mv = d_mv; gp.Nv = d_lv; gp.Kv = d_lv;
