@@ -257,3 +257,73 @@ def test_c2_ensemble_shape_subset_parity(cuda):
         dmu, dD = compare_members(res.mu[k, :ms[k]], res.D[k, :ms[k]], mu_o, D_o)
         assert dmu < TOL and dD < TOL, (ms[k], dmu, dD)
         assert np.allclose(res.sing_vals[k, :ms[k]], info_o.singular_values, rtol=1e-8, atol=1e-12)
+
+
+def test_bidiag_stage_entry(cuda):
+    """Blocked Householder bidiagonalisation through llck_bidiag_test: A = Q B P^H with B REAL upper bidiagonal."""
+    torch = cuda
+    from llckbdm_b200 import _native
+    from oracle.kbdm_oracle import brain_sim, hankel_matrices
+    lib = _native.load()
+    dev = torch.device("cuda:0")
+    for m in (1, 2, 31, 33, 100, 257):
+        ld = lib.llck_leading_dim(m)
+        if m <= 33:
+            rng = np.random.default_rng(m)
+            A = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
+        else:
+            A, _, _ = hankel_matrices(brain_sim(2 * m + 8, 1e-3, 0), m, 1)
+        Ap = np.zeros((ld, ld), dtype=complex)
+        Ap[:m, :m] = A
+        Ad = torch.from_numpy(np.ascontiguousarray(Ap.T).view(np.float64)).to(dev)
+        Qd = torch.zeros((ld, ld, 2), dtype=torch.float64, device=dev)
+        Pd = torch.zeros_like(Qd)
+        dd = torch.zeros(ld, dtype=torch.float64, device=dev)
+        ed = torch.zeros(ld, dtype=torch.float64, device=dev)
+        assert lib.llck_bidiag_test(Ad.data_ptr(), m, ld, dd.data_ptr(), ed.data_ptr(), Qd.data_ptr(), Pd.data_ptr(), None) == 0
+        Q = Qd.cpu().numpy().view(np.complex128)[..., 0].T[:m, :m]
+        P = Pd.cpu().numpy().view(np.complex128)[..., 0].T[:m, :m]
+        B = np.diag(dd.cpu().numpy()[:m]) + np.diag(ed.cpu().numpy()[:m - 1], 1)
+        scale = np.abs(A).max()
+        assert np.abs(Q @ B @ P.conj().T - A).max() < 1e-12 * scale
+        assert np.abs(Q.conj().T @ Q - np.eye(m)).max() < 1e-12 and np.abs(P.conj().T @ P - np.eye(m)).max() < 1e-12
+        s_ref = np.linalg.svd(A, compute_uv=False)
+        assert np.allclose(np.linalg.svd(B, compute_uv=False), s_ref, rtol=1e-9, atol=1e-12 * s_ref[0])
+
+
+@pytest.mark.parametrize("svd_mode", ["b", "j"])
+def test_both_svd_paths_tiny_and_ragged(cuda, svd_mode, monkeypatch):
+    """Tiny and ragged members (m = 1..65, l < m, p > 1, q > 0) through both SVD back ends:
+    'b' = bidiagonalisation + real Jacobi (default), 'j' = complex Jacobi on U directly."""
+    monkeypatch.setenv("LLCK_SVD", svd_mode)
+    from llckbdm_b200.ensemble import solve_ensemble
+    from llckbdm_b200.kbdm import kbdm
+    from oracle.kbdm_oracle import brain_sim, compare_members, kbdm_oracle, mu_from_line_list
+    c = brain_sim(2048, 1e-3, 7)
+    ms = [1, 2, 3, 5, 31, 32, 34, 65]
+    res = solve_ensemble(c, ms, ms, 1, 0.0, DWELL)
+    assert (res.status == 0).all()
+    for k, m in enumerate(ms):
+        _, info, mu, D = kbdm_oracle(c, DWELL, m=m, return_mu=True)
+        dmu, dD = compare_members(res.mu[k, :m], res.D[k, :m], mu, D)
+        assert dmu < TOL and dD < TOL, (m, dmu, dD)
+        assert np.allclose(res.sing_vals[k, :m], info.singular_values, rtol=1e-8, atol=1e-12)
+    for (m, l, p, q) in [(64, 1, 1, 0.0), (40, 2, 3, 0.0), (100, 7, 1, 1e-2), (33, 33, 4, 0.0)]:
+        ll, _ = kbdm(c, DWELL, m=m, l=l, p=p, q=q)
+        _, _, mu, D = kbdm_oracle(c, DWELL, m=m, l=l, p=p, q=q, return_mu=True)
+        dmu, dD = compare_members(mu_from_line_list(ll, DWELL), ll[:, 0] * np.exp(1j * ll[:, 3]), mu, D)
+        assert dmu < TOL and dD < TOL, (m, l, p, q, dmu, dD)
+
+
+def test_noiseless_rank_deficient_input_true_components(cuda):
+    """Noiseless brain_sim (numerical rank 16, cond ~1e18): kernels must not NaN/hang; the 16 true components match the
+    oracle (spurious poles are not reproducible between any two implementations)."""
+    from llckbdm_b200.kbdm import kbdm
+    from oracle.kbdm_oracle import BRAIN_SIM_PARAMS, brain_sim
+    ll, info = kbdm(brain_sim(2048, 0.0, 0), DWELL, m=512)
+    assert np.isfinite(ll[:, [0, 2, 3]]).all()
+    est = ll[(ll[:, 0] > 1e-4) & (ll[:, 1] > 0)]
+    est = est[np.argsort(est[:, 2])]
+    assert len(est) == 16
+    assert np.allclose(est[:, 0], BRAIN_SIM_PARAMS[:, 0], rtol=1e-6)
+    assert np.allclose(est[:, 2], BRAIN_SIM_PARAMS[:, 2], atol=1e-6)
