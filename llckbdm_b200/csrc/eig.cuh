@@ -340,8 +340,14 @@ __device__ __noinline__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, 
     const int lane = threadIdx.x & 31;
     int ihi = n - 1, its = 0, total = 0;
     while (ihi >= 0) {
-        int ilo = ihi;
-        while (ilo > 0 && !negligible_sub(Hs[ilo + ldh * (ilo - 1)], Hs[(ilo - 1) + ldh * (ilo - 1)], Hs[ilo + ldh * ilo])) --ilo;
+        // largest k in [1, ihi] with a negligible subdiagonal entry (lane-parallel scan, 32 candidates per ballot)
+        int ilo = 0;
+        for (int base = ihi; base >= 1 && ilo == 0; base -= 32) {
+            const int k = base - lane;
+            const bool neg = (k >= 1) && negligible_sub(Hs[k + ldh * (k - 1)], Hs[(k - 1) + ldh * (k - 1)], Hs[k + ldh * k]);
+            const unsigned bal = __ballot_sync(0xffffffffu, neg);
+            if (bal) ilo = base - (__ffs(bal) - 1);
+        }
         if (ilo > 0) {
             if (lane == 0) Hs[ilo + ldh * (ilo - 1)] = mkc(0.0, 0.0);
             __syncwarp();
