@@ -93,6 +93,14 @@ int llck_zgemm(int32_t amode, const void* A, int32_t lda, const void* B, int32_t
  * Q, P [dev] ld x m complex.  Allocates its own scratch (test helper, not part of the hot path). */
 int llck_bidiag_test(void* A, int32_t m, int32_t ld, double* d_out, double* e_out, void* Q, void* P, void* stream);
 
+/* Stage entry (tests): divide-and-conquer SVD of `batch` real upper-bidiagonal matrices (second half of the replacement of
+ * scipy.linalg.svd, llckbdm/kbdm.py:166).  d, e: device [batch][ld] (diagonal m, super-diagonal m-1); m: host [batch];
+ * ld multiple of 64.  Outputs (device): sing_vals [batch][ld] descending, Us = U*diag(s) and V as complex128 [batch][ld*ld]
+ * column-major with zero imaginary parts, fallback [batch] = 1 for members the solver leaves to the Jacobi path
+ * (numerically rank deficient).  Synchronous. */
+int llck_bdc_test(const double* d, const double* e, const int32_t* m, int32_t batch, int32_t ld,
+                  double* sing_vals, void* Us, void* V, int32_t* fallback, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ SYMBOLS = (
     "llck_kbdm_batched",
     "llck_zgemm",
     "llck_bidiag_test",
+    "llck_bdc_test",
 )
 
 FLAG_DEBUG_KEEP = 1
@@ -70,6 +71,8 @@ def load():
     lib.llck_zgemm.argtypes = [c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
     lib.llck_bidiag_test.restype = c_int
     lib.llck_bidiag_test.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.llck_bdc_test.restype = c_int
+    lib.llck_bdc_test.argtypes = [c_vp, c_vp, ctypes.POINTER(c_int), c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
     _lib = lib
     return lib
 

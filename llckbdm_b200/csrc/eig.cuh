@@ -679,7 +679,7 @@ __device__ __forceinline__ int block_max_int(int v, int* scratch) {
 }
 
 // status: 0 ok, 1 = QR did not converge
-__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out, long long* prof) {
+__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out, long long* prof, int max_trains) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* Hw = reinterpret_cast<cplx*>(smem_raw);
     cplx* Ww = Hw + E_MAT;
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
         ++its;
         if (its > 60) { failed = true; break; }
         // ---- aggressive early deflation on the trailing E_NW x E_NW window; its undeflated eigenvalues are the shifts ----
-        int nbu = E_NB;
+        int nbu = E_NB, ntrains = 1, ns_all = E_NB;
         {
             const int nw = E_NW;                      // size > E_W >= E_NW
             const int kwtop = ihi - nw + 1;
@@ -778,11 +778,17 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 }
                 __syncthreads();
             } else {
+                // all ns undeflated window eigenvalues are used as shifts: trains of <= E_NB bulges, one sweep per train
+                ns_all = ns;
+                ntrains = min(max_trains, (ns + E_NB - 1) / E_NB);
                 nbu = min(ns, E_NB);
             }
         }
-        // ---- one multishift sweep over [ilo, ihi] ----
+        // ---- one multishift sweep over [ilo, ihi] per train of shifts ----
         PROF(0);
+        for (int train = 0; train < ntrains; ++train) {
+        const cplx* tshifts = shifts + train * E_NB;
+        if (ntrains > 1) nbu = min(ns_all - train * E_NB, E_NB);
         ++nsweeps;
         int tstep = 0;
         while (true) {
@@ -810,7 +816,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 double c = 1.0; cplx s = mkc(0.0, 0.0);
                 if (active) {
                     cplx x, y;
-                    if (p == ilo - 1) { x = csub(Hw[(ilo - ws) + E_LDW * (ilo - ws)], shifts[warp]); y = Hw[(ilo + 1 - ws) + E_LDW * (ilo - ws)]; }
+                    if (p == ilo - 1) { x = csub(Hw[(ilo - ws) + E_LDW * (ilo - ws)], tshifts[warp]); y = Hw[(ilo + 1 - ws) + E_LDW * (ilo - ws)]; }
                     else { x = Hw[(p + 1 - ws) + E_LDW * (p - ws)]; y = Hw[(p + 2 - ws) + E_LDW * (p - ws)]; }
                     givens(x, y, c, s);
                     const cplx cs = cconj(s);
@@ -852,6 +858,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             apply_window_transform(Hb, Zb, ld, n, ws, we, Ww, tiles, iscr + 40);
             PROF(4);
             tstep += T;
+        }
         }
     }
     if (tid == 0) {

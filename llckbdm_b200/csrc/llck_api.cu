@@ -14,6 +14,7 @@
 #include "eig.cuh"
 #include "bidiag.cuh"
 #include "svd_real.cuh"
+#include "bdc.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -59,9 +60,17 @@ __global__ void mark_unconverged_kernel(const int* done, int* status, int batch)
     if (b < batch && !done[b]) atomicMax(&status[b], LLCK_STATUS_SVD_NOCONV);
 }
 
+// members flagged by the divide-and-conquer SVD are the only ones the Jacobi path still has to solve
+__global__ void bdc_fallback_count_kernel(const int* fallback, int* done, int* count, int batch) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    done[b] = fallback[b] ? 0 : 1;
+    if (fallback[b]) atomicAdd(count, 1);
+}
+
 // ---- workspace layout -----------------------------------------------------------------------------
 struct WsLayout {
-    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, mats, total;
+    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, bdcvec, fallback, mats, total;
     int nmats;
 };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -93,8 +102,12 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
     L.skip = o; o = al256(o + sizeof(int) * (size_t)batch * pairs_max);
     L.gws = o; o = al256(o + sizeof(cplx) * (size_t)batch * pairs_max * 2080);
     L.offws = o; o = al256(o + sizeof(double) * (size_t)batch * pairs_max);
+    L.bdcvec = o; o = al256(o + bdc_vec_bytes(batch, 2 * ld));
+    L.fallback = o; o = al256(o + sizeof(int) * batch);
     L.mats = o;
-    L.nmats = (flags & LLCK_FLAG_DEBUG_KEEP) ? 14 : 6;
+    // 6 pipeline matrices (14 in debug mode) + 5 for the divide-and-conquer SVD of the bidiagonal (two 2ld x 2ld real
+    // eigenvector buffers and the secular eigenvector matrices)
+    L.nmats = ((flags & LLCK_FLAG_DEBUG_KEEP) ? 14 : 6) + 5;
     o += (size_t)L.nmats * batch * ld * ld * sizeof(cplx);
     L.total = o;
     return L;
@@ -221,6 +234,40 @@ int llck_bidiag_test(void* A, int32_t m, int32_t ld, double* d_out, double* e_ou
     return e2 == cudaSuccess ? 0 : -(int)e2;
 }
 
+int llck_bdc_test(const double* d, const double* e, const int32_t* m, int32_t batch, int32_t ld,
+                  double* sing_vals, void* Us, void* V, int32_t* fallback, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d || !e || !m || batch <= 0 || ld <= 0 || (ld & 63)) return LLCK_E_BADARG;
+    int mmax = 0;
+    for (int b = 0; b < batch; ++b) { if (m[b] < 1 || m[b] > ld) return LLCK_E_BADARG; if (m[b] > mmax) mmax = m[b]; }
+    const size_t qbytes = sizeof(double) * (size_t)batch * 4 * ld * ld;
+    const size_t vbytes = bdc_vec_bytes(batch, 2 * ld);
+    unsigned char* w = nullptr;
+    CK(cudaMalloc(&w, 2 * qbytes + qbytes / 2 + vbytes + 2 * sizeof(int) * (size_t)batch + 1024));
+    BdcParams bp;
+    bp.dws = d; bp.ews = e; bp.ld = ld; bp.batch = batch; bp.ldq = 2 * ld;
+    bp.qstride = 4LL * ld * ld; bp.xstride = 2LL * ld * ld;
+    bp.Q[0] = (double*)w; bp.Q[1] = (double*)(w + qbytes); bp.X = (double*)(w + 2 * qbytes);
+    bdc_carve_vectors(bp, w + 2 * qbytes + qbytes / 2, batch, 2 * ld);
+    int* d_m = (int*)(w + 2 * qbytes + qbytes / 2 + vbytes);
+    int* d_status = d_m + batch;
+    bp.mv = d_m; bp.level = 0;
+    cudaError_t e1 = cudaMemcpyAsync(d_m, m, sizeof(int) * batch, cudaMemcpyHostToDevice, st);
+    if (e1 == cudaSuccess) e1 = cudaMemsetAsync(d_status, 0, sizeof(int) * batch, st);
+    int rc = (e1 == cudaSuccess) ? bdc_driver(bp, mmax, st) : -(int)e1;
+    if (rc == 0) {
+        bdc_sv_kernel<<<batch, 256, 0, st>>>(bp, sing_vals, ld, fallback);
+        dim3 grid(mmax, batch);
+        bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_m, sing_vals, ld, 0.0, (cplx*)Us, (cplx*)V, (long long)ld * ld, ld, d_status, fallback, 1);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) rc = -(int)e2;
+    }
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    cudaFree(w);
+    if (rc) return rc;
+    return e3 == cudaSuccess ? 0 : -(int)e3;
+}
+
 int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int32_t* m, const int32_t* l,
                       int32_t p, double q, double dwell, int32_t batch,
                       double* line_lists, int64_t ll_stride,
@@ -329,10 +376,37 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             if (rc) return rc;
         }
         TICK();   // 1: init + bidiagonalisation done
-        // (2) SVD of B by real block one-sided Jacobi
+        // (2) SVD of the real bidiagonal B: divide and conquer (default); members it flags as numerically rank deficient
+        //     (and every member with LLCK_SVD=b) go through the real block one-sided Jacobi
+        const bool use_dc = !(smode && smode[0] == 'b');
+        int* d_fallback = (int*)(ws + L.fallback);
+        int n_fallback = batch;
+        BdcParams bp;
+        if (use_dc) {
+            const int nb0 = dbg ? 14 : 6;
+            bp.dws = dws; bp.ews = ews; bp.ld = ld; bp.mv = d_mv; bp.batch = batch;
+            bp.ldq = 2 * ld; bp.qstride = 4 * stride; bp.xstride = 2 * stride;
+            bp.Q[0] = (double*)mat(nb0); bp.Q[1] = (double*)mat(nb0 + 2); bp.X = (double*)mat(nb0 + 4);
+            bdc_carve_vectors(bp, ws + L.bdcvec, batch, 2 * ld);
+            bp.level = 0;
+            int rc = bdc_driver(bp, mmax, st);
+            if (rc) return rc;
+            bdc_sv_kernel<<<batch, 256, 0, st>>>(bp, sing_vals, sv_stride, d_fallback);
+            dim3 grid(lmax, batch);
+            bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_lv, sing_vals, sv_stride, q, bLpre, bRpre, stride, ld, status, d_fallback, 0);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(d_nact, 0, sizeof(int), st));
+            bdc_fallback_count_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_fallback, d_done, d_nact, batch);
+            CK(cudaMemcpyAsync(&n_fallback, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            launches += 4 + 7 * 5;
+            if (verbose) fprintf(stderr, "[llck] bidiagonal D&C: %d of %d members fall back to the Jacobi SVD\n", n_fallback, batch);
+        }
+        const int* d_only = use_dc ? d_fallback : nullptr;
         double* Xr = (double*)bReal;
         double* Vr = Xr + (long long)ld * ld;
         const long long rstride = 2 * stride;       // doubles per member
+        if (n_fallback > 0) {
         {
             dim3 grid(256, batch);
             rsvd_init_kernel<<<grid, 256, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_nbv, dws, ews);
@@ -348,7 +422,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         rp.pairs_max = ((ld / J_B) + 1) / 2 + 1;
         cudaEvent_t uev[128];
         if (timing) for (int i = 0; i < 128; ++i) CK(cudaEventCreate(&uev[i]));
-        int h_active = batch;
+        int h_active = n_fallback;
         for (int sweep = 0; sweep < 30 && h_active > 0; ++sweep) {
             for (int r = 0; r < nbmax - 1; ++r) {
                 rp.round = r;
@@ -385,21 +459,23 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             }
         }
         if (timing) for (int i = 0; i < 128; ++i) cudaEventDestroy(uev[i]);
-        TICK();   // 2: jacobi done
         if (h_active > 0) {
             mark_unconverged_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_done, status, batch);
             CK(cudaGetLastError());
         }
-        // (3) singular values, truncation/scaling, back-multiplication by Q and P
+        // singular values, truncation/scaling of the Jacobi members
         int npow2 = 64;
         while (npow2 < ld) npow2 <<= 1;
-        rsvd_finalize_kernel<<<batch, 256, npow2 * 12, st>>>(Xr, rstride, ld, d_mv, d_nbv, sing_vals, sv_stride, d_perm, npow2);
+        rsvd_finalize_kernel<<<batch, 256, npow2 * 12, st>>>(Xr, rstride, ld, d_mv, d_nbv, sing_vals, sv_stride, d_perm, npow2, d_only);
         CK(cudaGetLastError());
         {
             dim3 grid(lmax, batch);
-            rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 0);
+            rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 0, d_only);
             CK(cudaGetLastError());
         }
+        }
+        TICK();   // 2: SVD of the bidiagonal done
+        // (3) back-multiplication by Q and P
         GemmParams g = gemm_params_zero();          // Lt = Q * Lpre
         g.A = bQ; g.strideA = stride; g.lda = ld; g.B = bLpre; g.strideB = stride; g.ldb = ld; g.C = bLt; g.strideC = stride; g.ldc = ld;
         g.Mv = d_mv; g.Nv = d_lv; g.Kv = d_mv;
@@ -410,7 +486,8 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             CK(cudaMemsetAsync(mat(0), 0, sizeof(cplx) * batch * stride, st));
             CK(cudaMemsetAsync(mat(1), 0, sizeof(cplx) * batch * stride, st));
             dim3 grid(mmax, batch);
-            rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 1);
+            if (n_fallback > 0) rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 1, d_only);
+            if (use_dc) bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_lv, sing_vals, sv_stride, q, bLpre, bRpre, stride, ld, status, d_fallback, 1);
             CK(cudaGetLastError());
             g.A = bQ; g.B = bLpre; g.C = mat(0); g.Nv = d_mv;
             CK(zgemm_batched(A_NORMAL, g, mmax, mmax, mmax, batch, st));
@@ -655,7 +732,9 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         CK(cudaFuncSetAttribute(hqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HQR_SMEM_BYTES));
         long long* d_prof = nullptr;
         if (verbose) { CK(cudaMalloc(&d_prof, sizeof(long long) * 6 * batch)); }
-        hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof);
+        int hqr_trains = 1;
+        if (const char* ev = getenv("LLCK_HQR_TRAINS")) hqr_trains = atoi(ev) > 1 ? 2 : 1;
+        hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains);
         CK(cudaGetLastError());
         if (verbose) {
             long long* hp = (long long*)malloc(sizeof(long long) * 6 * batch);

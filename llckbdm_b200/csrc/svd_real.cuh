@@ -352,11 +352,13 @@ __global__ void __launch_bounds__(256, 2) rjacobi_update_kernel(RJacobiParams p)
 
 // column norms of X -> singular values sorted descending + permutation (real twin of svd_finalize_kernel)
 __global__ void __launch_bounds__(256) rsvd_finalize_kernel(const double* X, long long stride, int ld, const int* mv, const int* nbv,
-                                                            double* sing_vals, long long sv_stride, int* perm_out, int npow2) {
+                                                            double* sing_vals, long long sv_stride, int* perm_out, int npow2,
+                                                            const int* only = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* key = reinterpret_cast<double*>(smem_raw);
     int* val = reinterpret_cast<int*>(key + npow2);
     const int b = blockIdx.x, m = mv[b], mp = nbv[b] * J_B;
+    if (only && !only[b]) return;          // member already solved by the divide-and-conquer path
     const double* Xb = X + (long long)b * stride;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int j = warp; j < npow2; j += 8) {
@@ -394,10 +396,12 @@ __global__ void __launch_bounds__(256) rsvd_finalize_kernel(const double* X, lon
 // With scale_mode = 1 the columns are left unscaled except X / 1 (debug: X_dbg = Q * X, V_dbg = P * V).
 __global__ void rsvd_gather_kernel(const double* X, const double* V, long long rstride, int ld, const int* mv, const int* lv,
                                    const double* sing_vals, long long sv_stride, const int* perm, double q,
-                                   cplx* Lpre, cplx* Rpre, long long cstride, int* status, int scale_mode) {
+                                   cplx* Lpre, cplx* Rpre, long long cstride, int* status, int scale_mode,
+                                   const int* only = nullptr) {
     const int b = blockIdx.y, k = blockIdx.x;
     const int m = mv[b], l = scale_mode ? m : lv[b];
     if (k >= l) return;
+    if (only && !only[b]) return;
     const int src = perm[(long long)b * ld + k];
     double fx = 1.0, fv = 1.0;
     if (!scale_mode) {
