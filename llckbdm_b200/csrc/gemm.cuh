@@ -180,6 +180,72 @@ __global__ void __launch_bounds__(256) zgemm_batched_kernel(GemmParams p) {
     }
 }
 
+// Skinny variant for the block-reflector products W = (V T)^H X with M <= 32 rows (A stored K x M, used as conj(A)^T):
+// 32 x 128 tiles (the 64 x 64 tile would issue half of its DMMAs on padding rows).
+#define GW_BN 128
+#define GW_A_ELEMS (G_LDA_T * 32)
+#define GW_B_ELEMS (G_LDB * GW_BN)
+__global__ void __launch_bounds__(256) zgemm_w32_kernel(GemmParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* smem = reinterpret_cast<cplx*>(smem_raw);
+    const int b = blockIdx.z;
+    const int M = (p.Mv ? p.Mv[b] : 0) + p.Mc, N = (p.Nv ? p.Nv[b] : 0) + p.Nc;
+    int K = (p.Kv ? p.Kv[b] : 0) + p.Kc;
+    if (p.Kcap > 0 && K > p.Kcap) K = p.Kcap;
+    const int col0 = blockIdx.y * GW_BN;
+    if (M <= 0 || col0 >= N || K <= 0) return;
+    cplx* As[2] = {smem, smem + GW_A_ELEMS};
+    cplx* Bs[2] = {smem + 2 * GW_A_ELEMS, smem + 2 * GW_A_ELEMS + GW_B_ELEMS};
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int wr = warp >> 2, wc = warp & 3;        // warp tile: rows 16*wr.., cols 32*wc..
+    const cplx* Ag = p.A + (long long)b * p.strideA;
+    const cplx* Bg = p.B + (long long)b * p.strideB;
+    cplx* Cg = p.C + (long long)b * p.strideC;
+    auto load_tiles = [&](int buf, int k0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            int idx = tid + 256 * r;
+            int k = idx & 15, i = idx >> 4;
+            bool ok = (i < M) && (k0 + k < K);
+            const cplx* src = ok ? (Ag + (k0 + k) + (long long)p.lda * i) : Ag;
+            cp_async16(&As[buf][k + G_LDA_T * i], src, ok);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int idx = tid + 256 * r;
+            int k = idx & 15, j = idx >> 4;
+            bool ok = (col0 + j < N) && (k0 + k < K);
+            const cplx* src = ok ? (Bg + (k0 + k) + (long long)p.ldb * (col0 + j)) : Bg;
+            cp_async16(&Bs[buf][k + G_LDB * j], src, ok);
+        }
+        cp_async_commit();
+    };
+    double acc[2][4][4];
+    zero_acc<2, 4>(acc);
+    const int nk = (K + G_BK - 1) / G_BK;
+    load_tiles(0, 0);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) { load_tiles(buf ^ 1, (kt + 1) * G_BK); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        warp_zmma<2, 4, true, false>(acc, As[buf] + G_LDA_T * (16 * wr), G_LDA_T, 1, Bs[buf] + G_LDB * (32 * wc), 1, G_LDB, G_BK);
+        __syncthreads();
+    }
+    const int lane = tid & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = 16 * wr + 8 * i + g;
+        if (r >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = col0 + 32 * wc + 8 * j + 2 * t;
+            if (c < N) Cg[r + (long long)p.ldc * c] = mkc(acc[i][j][0], acc[i][j][2]);
+            if (c + 1 < N) Cg[r + (long long)p.ldc * (c + 1)] = mkc(acc[i][j][1], acc[i][j][3]);
+        }
+    }
+}
+
 static inline size_t zgemm_smem_bytes(int amode, int Kmax) {
     if (amode == A_HANKEL) return (size_t)(2 * G_B_ELEMS + G_SIG_MAX) * sizeof(cplx);
     return (size_t)(2 * G_A_ELEMS + 2 * G_B_ELEMS) * sizeof(cplx);
@@ -201,6 +267,14 @@ static inline cudaError_t zgemm_batched(int amode, const GemmParams& p, int Mmax
     size_t smem = zgemm_smem_bytes(amode, Kmax);
     if (amode == A_NORMAL && breal) return zgemm_launch<A_NORMAL, false, true>(p, grid, smem, stream);
     if (amode == A_NORMAL) return bconjt ? zgemm_launch<A_NORMAL, true>(p, grid, smem, stream) : zgemm_launch<A_NORMAL, false>(p, grid, smem, stream);
+    if (amode == A_CONJT && Mmax <= 32 && !p.accum && !p.triB) {
+        const size_t sm32 = (size_t)(2 * GW_A_ELEMS + 2 * GW_B_ELEMS) * sizeof(cplx);
+        cudaError_t e = cudaFuncSetAttribute(zgemm_w32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32);
+        if (e != cudaSuccess) return e;
+        dim3 g32(1, (Nmax + GW_BN - 1) / GW_BN, batch);
+        zgemm_w32_kernel<<<g32, 256, sm32, stream>>>(p);
+        return cudaGetLastError();
+    }
     if (amode == A_CONJT) return zgemm_launch<A_CONJT, false>(p, grid, smem, stream);
     if (64 + Kmax + 32 > G_SIG_MAX) return cudaErrorInvalidValue;
     return zgemm_launch<A_HANKEL, false>(p, grid, smem, stream);

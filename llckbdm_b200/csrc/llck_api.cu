@@ -399,7 +399,11 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             bdc_fallback_count_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_fallback, d_done, d_nact, batch);
             CK(cudaMemcpyAsync(&n_fallback, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            launches += 4 + 7 * 5;
+            {
+                int lvmax = 0;
+                while ((1 << lvmax) < bdc_nleaf(mmax)) ++lvmax;
+                launches += 2 + 7 * lvmax + 3;     // init, leaves, 7 kernels per merge level, singular values, gather, fallback count
+            }
             if (verbose) fprintf(stderr, "[llck] bidiagonal D&C: %d of %d members fall back to the Jacobi SVD\n", n_fallback, batch);
         }
         const int* d_only = use_dc ? d_fallback : nullptr;
@@ -821,7 +825,19 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             if (e3 != cudaSuccess) return -(int)e3;
         }
         info[0] = sweeps_run; info[1] = h_maxs; info[2] = ld; info[3] = nbmax;
-        info[13] = launches + 2 /*finalize, gather*/ + 5 /*gemms*/ + 3 /*hessenberg, hqr, trevc*/ + 1 /*epilogue*/;
+        // kernel launches of this call (panel loops counted from their trip counts)
+        const int nbp = (mmax + BD_NB - 1) / BD_NB;                       // bidiagonalisation panels
+        const int nhp = lmax > 2 ? (lmax - 2 + HB_NB - 1) / HB_NB : 0;    // Hessenberg panels
+        const int ntb = (lmax - 1) / TV_NB + 1;                           // trevc blocks
+        int total = launches;
+        if (svd_bidiag) total += nbp + (nbp - 1) + 2 + 2 * nbp * 3 + 2;   // panels, trailing updates, Q/P accumulation, back-multiplication
+        else total += 2;                                                  // finalize, gather
+        total += 2;                                                       // T1, Ured
+        total += nhp + 3 * (nhp > 0 ? nhp - 1 : 0) + 1 + 3 * nhp + 1;     // Hessenberg panels + updates, identity, Q accumulation, clear
+        total += 1;                                                       // hqr
+        total += 1 + ntb + (ntb - 1) + 1;                                 // trevc
+        total += 3 + 1;                                                   // P, B, W, epilogue
+        info[13] = total;
         info[14] = jac_rounds;   // Jacobi rounds (one gram + eig + update launch each)
         info[15] = (upd_launches > 0) ? (int32_t)(upd_us / upd_launches) : 0;   // avg jacobi_update_kernel duration (us), timing mode
     }

@@ -291,10 +291,10 @@ def test_bidiag_stage_entry(cuda):
         assert np.allclose(np.linalg.svd(B, compute_uv=False), s_ref, rtol=1e-9, atol=1e-12 * s_ref[0])
 
 
-@pytest.mark.parametrize("svd_mode", ["b", "j"])
+@pytest.mark.parametrize("svd_mode", ["d", "b", "j"])
 def test_both_svd_paths_tiny_and_ragged(cuda, svd_mode, monkeypatch):
-    """Tiny and ragged members (m = 1..65, l < m, p > 1, q > 0) through both SVD back ends:
-    'b' = bidiagonalisation + real Jacobi (default), 'j' = complex Jacobi on U directly."""
+    """Tiny and ragged members (m = 1..65, l < m, p > 1, q > 0) through all SVD back ends: 'd' = bidiagonalisation +
+    divide and conquer (default), 'b' = bidiagonalisation + real Jacobi, 'j' = complex Jacobi on U directly."""
     monkeypatch.setenv("LLCK_SVD", svd_mode)
     from llckbdm_b200.ensemble import solve_ensemble
     from llckbdm_b200.kbdm import kbdm
@@ -313,6 +313,63 @@ def test_both_svd_paths_tiny_and_ragged(cuda, svd_mode, monkeypatch):
         _, _, mu, D = kbdm_oracle(c, DWELL, m=m, l=l, p=p, q=q, return_mu=True)
         dmu, dD = compare_members(mu_from_line_list(ll, DWELL), ll[:, 0] * np.exp(1j * ll[:, 3]), mu, D)
         assert dmu < TOL and dD < TOL, (m, l, p, q, dmu, dD)
+
+
+def test_bdc_stage_entry(cuda):
+    """Divide-and-conquer SVD of real bidiagonals through llck_bdc_test: ragged batch (one leaf ... five merge levels),
+    gaussian / graded / clustered / split / diagonal inputs, against numpy.linalg.svd."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from bdc_check import run_bdc
+    rng = np.random.default_rng(3)
+    ds, es = [], []
+    for m in (1, 2, 17, 32, 33, 64, 65, 130, 257):
+        ds.append(rng.standard_normal(m) + 3.0); es.append(rng.standard_normal(m - 1))      # well conditioned
+    for m in (96, 300, 512):
+        g = np.logspace(0, -4, m)
+        ds.append(g * (2.0 + rng.random(m))); es.append(0.3 * g[:-1] * rng.standard_normal(m - 1))   # graded
+        ds.append(np.ones(m)); es.append(np.full(m - 1, 1e-3))                                       # clustered
+        d = rng.standard_normal(m) + 3.0; e = rng.standard_normal(m - 1); e[m // 3] = 0.0
+        ds.append(d); es.append(e)                                                                   # exact split
+        ds.append(np.arange(1, m + 1, dtype=float)); es.append(np.zeros(m - 1))                      # diagonal
+    solved = 0
+    for (s, Us, V, fb), d, e in zip(run_bdc(ds, es), ds, es):
+        m = len(d)
+        B = np.diag(d) + np.diag(e, 1)
+        s_ref = np.linalg.svd(B, compute_uv=False)
+        if fb:      # only numerically rank-deficient members may be handed to the Jacobi path
+            assert s_ref[-1] < 1e-7 * s_ref[0]
+            continue
+        solved += 1
+        cond = s_ref[0] / s_ref[-1]
+        assert np.abs(s - s_ref).max() < 1e-13 * s_ref[0]
+        U = Us / s
+        assert np.abs(U.T @ U - np.eye(m)).max() < 1e-14 * max(cond, 100.0)
+        assert np.abs(V.T @ V - np.eye(m)).max() < 1e-14 * max(cond, 100.0)
+        assert np.abs(B - Us @ V.T).max() < 1e-13 * s_ref[0]
+    assert solved >= 18
+
+
+def test_mixed_batch_rank_deficient_member_falls_back_to_jacobi(cuda):
+    """One batch holding a noiseless (numerically rank-16) FID next to noisy ones: the divide-and-conquer SVD flags the
+    rank-deficient member, the Jacobi path solves it, and the noisy members keep full parity."""
+    from llckbdm_b200.ensemble import solve_ensemble
+    from oracle.kbdm_oracle import BRAIN_SIM_PARAMS, brain_sim, compare_members, kbdm_oracle
+    sigs = [brain_sim(512, 1e-3, 1), brain_sim(512, 0.0, 0), brain_sim(512, 1e-3, 2)]
+    ms = [200, 256, 130]
+    res = solve_ensemble(sigs, ms, ms, 1, 0.0, DWELL)
+    assert (res.status == 0).all()
+    for k in (0, 2):
+        _, info, mu, D = kbdm_oracle(sigs[k], DWELL, m=ms[k], return_mu=True)
+        dmu, dD = compare_members(res.mu[k, :ms[k]], res.D[k, :ms[k]], mu, D)
+        assert dmu < TOL and dD < TOL, (k, dmu, dD)
+        assert np.allclose(res.sing_vals[k, :ms[k]], info.singular_values, rtol=1e-8, atol=1e-12)
+    ll = res.line_lists[1, :ms[1]]
+    est = ll[(ll[:, 0] > 1e-4) & (ll[:, 1] > 0)]
+    est = est[np.argsort(est[:, 2])]
+    assert len(est) == 16
+    assert np.allclose(est[:, 0], BRAIN_SIM_PARAMS[:, 0], rtol=1e-6)
+    assert np.allclose(est[:, 2], BRAIN_SIM_PARAMS[:, 2], atol=1e-6)
 
 
 def test_noiseless_rank_deficient_input_true_components(cuda):
