@@ -93,6 +93,17 @@ int llck_zgemm(int32_t amode, const void* A, int32_t lda, const void* B, int32_t
  * Q, P [dev] ld x m complex.  Allocates its own scratch (test helper, not part of the hot path). */
 int llck_bidiag_test(void* A, int32_t m, int32_t ld, double* d_out, double* e_out, void* Q, void* P, void* stream);
 
+/* Frequency-domain RMSE of `batch` candidate line lists against one FID -- replaces the scoring loop of
+ * llckbdm/min_rmse_kbdm.py:33-41 (calculate_freq_domain_rmse, llckbdm/metrics.py:7-17: multi_fid synthesis on
+ * t = n*dwell, fft/sqrt(N) of data and model, RMSE of the REAL parts).  Stream-ordered, asynchronous, allocates nothing.
+ *   data        device complex128 [N]
+ *   line_lists  device float64 [batch][ll_stride], rows (A, T2, F, PH) as written by llck_kbdm_batched
+ *   n_rows      device int32 [batch]: rows of each candidate
+ *   filter      1: skip rows failing  A > amplitude_tol and T2 > 0  (filter_samples, llckbdm/sampling.py:75-97)
+ *   rmse_out    device float64 [batch]; +inf for a candidate without valid rows (min_rmse_kbdm.py:36-37)            */
+int llck_rmse_batched(const void* data, int32_t N, double dwell, const double* line_lists, int64_t ll_stride,
+                      const int32_t* n_rows, int32_t batch, int32_t filter, double amplitude_tol, double* rmse_out, void* stream);
+
 /* Stage entry (tests): divide-and-conquer SVD of `batch` real upper-bidiagonal matrices (second half of the replacement of
  * scipy.linalg.svd, llckbdm/kbdm.py:166).  d, e: device [batch][ld] (diagonal m, super-diagonal m-1); m: host [batch];
  * ld multiple of 64.  Outputs (device): sing_vals [batch][ld] descending, Us = U*diag(s) and V as complex128 [batch][ld*ld]

@@ -15,6 +15,7 @@
 #include "bidiag.cuh"
 #include "svd_real.cuh"
 #include "bdc.cuh"
+#include "rmse.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -232,6 +233,18 @@ int llck_bidiag_test(void* A, int32_t m, int32_t ld, double* d_out, double* e_ou
     cudaFree(w); cudaFree(dd);
     if (rc) return rc;
     return e2 == cudaSuccess ? 0 : -(int)e2;
+}
+
+int llck_rmse_batched(const void* data, int32_t N, double dwell, const double* line_lists, int64_t ll_stride,
+                      const int32_t* n_rows, int32_t batch, int32_t filter, double amplitude_tol, double* rmse_out, void* stream) {
+    if (!data || !line_lists || !n_rows || !rmse_out || N < 1 || batch < 1 || !(dwell > 0.0) || ll_stride < 4) return LLCK_E_BADARG;
+    const size_t sm = sizeof(cplx) * (size_t)N;
+    if (sm > 200 * 1024) return LLCK_E_BADARG;            // model FID is staged in shared memory (N <= 12800)
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaFuncSetAttribute(rmse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    rmse_kernel<<<batch, RMSE_THREADS, sm, st>>>((const cplx*)data, N, dwell, line_lists, ll_stride, n_rows, filter, amplitude_tol, rmse_out);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 int llck_bdc_test(const double* d, const double* e, const int32_t* m, int32_t batch, int32_t ld,

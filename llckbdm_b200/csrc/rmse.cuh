@@ -1,0 +1,54 @@
+// Frequency-domain RMSE scoring of candidate line lists -- replaces the per-candidate loop of reference
+// llckbdm/min_rmse_kbdm.py:33-41 and llckbdm/metrics.py:7-17 (multi_fid synthesis, two FFTs, RMSE of the real parts).
+//
+// No FFT is needed: Re FFT(r)_k = FFT(r_e)_k with r_e[n] = (r[n] + conj(r[(N-n) mod N])) / 2, so by Parseval
+//   mean_k (Re FFT(r)_k / sqrt N)^2 = (1/N) sum_n |r_e[n]|^2,      r = data - model.
+// One CTA per candidate: the model FID sum_k A_k exp(-t/T2_k) exp(i(2 pi F_k t + PH_k)) is synthesised in shared memory
+// (thread t evaluates exp/sincos once per component at n = t and walks n = t + 256 j with the complex ratio mu^256),
+// the row filter of sampling.py:75-97 (A > tol and T2 > 0) is applied on the fly, then one block reduction.
+#pragma once
+#include "common.cuh"
+
+#define RMSE_THREADS 256
+
+__global__ void __launch_bounds__(RMSE_THREADS) rmse_kernel(const cplx* __restrict__ data, int N, double dwell,
+                                                            const double* __restrict__ ll, long long ll_stride,
+                                                            const int* __restrict__ nrows, int filter, double amp_tol,
+                                                            double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* model = reinterpret_cast<cplx*>(smem_raw);       // N
+    __shared__ double red[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int rows = nrows[b];
+    const double* L = ll + (long long)b * ll_stride;
+    for (int n = tid; n < N; n += RMSE_THREADS) model[n] = mkc(0.0, 0.0);
+    const double t0 = tid * dwell, ts = RMSE_THREADS * dwell;
+    const double twopi = 6.283185307179586476925286766559;
+    int nvalid = 0;
+    for (int k = 0; k < rows; ++k) {
+        const double A = L[4 * k], T2 = L[4 * k + 1], F = L[4 * k + 2], PH = L[4 * k + 3];
+        if (filter && !(A > amp_tol && T2 > 0.0)) continue;
+        ++nvalid;
+        double sn, cs;
+        sincos(twopi * F * t0 + PH, &sn, &cs);
+        const double mag = A * exp(-t0 / T2);
+        cplx z = mkc(mag * cs, mag * sn);
+        sincos(twopi * F * ts, &sn, &cs);
+        const double ms = exp(-ts / T2);
+        const cplx step = mkc(ms * cs, ms * sn);
+        for (int n = tid; n < N; n += RMSE_THREADS) {        // each thread owns its own n's: no conflicts
+            model[n] = cadd(model[n], z);
+            z = cmul(z, step);
+        }
+    }
+    __syncthreads();
+    double sum = 0.0;
+    for (int n = tid; n < N; n += RMSE_THREADS) {
+        const int n2 = (n == 0) ? 0 : N - n;
+        const cplx r = csub(data[n], model[n]), r2 = csub(data[n2], model[n2]);
+        const double x = 0.5 * (r.x + r2.x), y = 0.5 * (r.y - r2.y);
+        sum = fma(x, x, fma(y, y, sum));
+    }
+    sum = block_sum(sum, red);
+    if (tid == 0) out[b] = (nvalid > 0) ? sqrt(sum / (double)N) : INFINITY;
+}

@@ -39,7 +39,7 @@ def lpt_shards(costs, world_size):
 class EnsembleResult:
     """Padded, fixed-stride results of a batch (host numpy arrays)."""
 
-    def __init__(self, line_lists, mu, D, sing_vals, n_valid, status, m, l, info=None):
+    def __init__(self, line_lists, mu, D, sing_vals, n_valid, status, m, l, info=None, rmse=None):
         self.line_lists = line_lists    # float64 [M, lmax, 4]
         self.mu = mu                    # complex128 [M, lmax]
         self.D = D                      # complex128 [M, lmax]
@@ -49,6 +49,7 @@ class EnsembleResult:
         self.m = m
         self.l = l
         self.info = info or {}
+        self.rmse = rmse                # float64 [M] frequency-domain RMSE of each member's filtered line list (if requested)
 
 
 def _require_cuda():
@@ -108,6 +109,44 @@ def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=
                 info=list(info), workspace=workspace, ld=ld)
 
 
+def score_rmse_device(data_dev, dwell, line_lists_dev, n_rows_dev, filter_rows=True, amplitude_tol=1e-6, stream=None):
+    """Frequency-domain RMSE of every candidate line list against one FID, on the device (llck_rmse_batched; replaces the
+    loop of reference min_rmse_kbdm.py:33-41 over metrics.py:7-17).
+
+    data_dev: complex128 CUDA tensor [N]; line_lists_dev: float64 CUDA tensor [batch, rows_max, 4];
+    n_rows_dev: int32 CUDA tensor [batch].  Returns a float64 CUDA tensor [batch] (+inf where no row is valid)."""
+    torch = _require_cuda()
+    lib = _native.load()
+    batch = line_lists_dev.shape[0]
+    dev = data_dev.device
+    out = torch.empty(batch, dtype=torch.float64, device=dev)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    rc = lib.llck_rmse_batched(data_dev.data_ptr(), int(data_dev.numel()), float(dwell), line_lists_dev.data_ptr(),
+                               int(line_lists_dev.shape[1]) * 4, n_rows_dev.data_ptr(), batch, 1 if filter_rows else 0,
+                               float(amplitude_tol), out.data_ptr(), st.cuda_stream)
+    _native.check_rc(rc, "llck_rmse_batched")
+    return out
+
+
+def score_candidates(data, dwell, candidates, filter_rows=False, device=None):
+    """Host lists in, host RMSE list out: packs the candidate line lists, one H2D copy, one kernel, one D2H copy."""
+    torch = _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    M = len(candidates)
+    if M == 0:
+        return []
+    rows = np.array([len(c) for c in candidates], dtype=np.int32)
+    rmax = max(1, int(rows.max()))
+    packed = np.zeros((M, rmax, 4))
+    for i, c in enumerate(candidates):
+        if rows[i] > 0:
+            packed[i, :rows[i]] = np.asarray(c, dtype=np.float64).reshape(-1, 4)
+    with torch.cuda.device(dev):
+        d_dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.complex128).view(np.float64)).to(dev).view(torch.complex128)
+        out = score_rmse_device(d_dev, dwell, torch.from_numpy(packed).to(dev), torch.from_numpy(rows).to(dev), filter_rows=filter_rows)
+        return [float(x) for x in out.cpu().numpy()]
+
+
 def flatten_signals(signals, M):
     """One shared 1-D FID, or a list of M FIDs -> (flat complex128 array, int64 offsets)."""
     if isinstance(signals, np.ndarray) and signals.ndim == 1:
@@ -120,11 +159,13 @@ def flatten_signals(signals, M):
     return np.concatenate(sigs), offsets
 
 
-def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None):
+def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None, score_rmse=False):
     """Solve an ensemble given HOST inputs; returns an ``EnsembleResult`` of host arrays.
 
     signals: either one 1-D complex array shared by all members, or a list of 1-D complex arrays (one per member).
     The host->device copy of the FIDs and the device->host copy of the results are part of this call.
+    score_rmse (one shared FID only): also score every member's FILTERED line list (A > 1e-6, T2 > 0) against the FID on the
+    device, straight from the solver's output buffer -> ``result.rmse``.
     """
     torch = _require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -145,6 +186,9 @@ def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None):
         out_sv = np.zeros((M, mmax))
         out_nv = np.zeros(M, dtype=np.int32)
         out_st = np.zeros(M, dtype=np.int32)
+        out_rm = np.full(M, np.inf) if score_rmse else None
+        if score_rmse and not (isinstance(signals, np.ndarray) and signals.ndim == 1):
+            raise ValueError("score_rmse needs one shared FID")
         ws = None
         infos = []
         # cost-sorted chunks keep similar sizes together (less padding work inside a launch)
@@ -160,5 +204,8 @@ def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None):
             out_sv[idx, :mm] = r["sing_vals"].cpu().numpy()
             out_nv[idx] = r["n_valid"].cpu().numpy()
             out_st[idx] = r["status"].cpu().numpy()
+            if score_rmse:
+                rows = torch.from_numpy(np.ascontiguousarray(l[idx], dtype=np.int32)).to(dev)
+                out_rm[idx] = score_rmse_device(sig_dev, dwell, r["line_lists"], rows, filter_rows=True).cpu().numpy()
             infos.append(r["info"])
-    return EnsembleResult(out_ll, out_mu, out_D, out_sv, out_nv, out_st, m, l, info={"chunks": infos, "ld": ld})
+    return EnsembleResult(out_ll, out_mu, out_D, out_sv, out_nv, out_st, m, l, info={"chunks": infos, "ld": ld}, rmse=out_rm)

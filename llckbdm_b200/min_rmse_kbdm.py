@@ -1,11 +1,14 @@
-"""Drop-in for reference llckbdm/min_rmse_kbdm.py: pick the candidate line list with minimum
-frequency-domain RMSE; candidates come from the batched GPU ``sample_kbdm`` unless given."""
+"""Drop-in for reference llckbdm/min_rmse_kbdm.py: pick the candidate line list with minimum frequency-domain RMSE.
+Candidates come from the batched GPU ``sample_kbdm`` unless given; the scoring loop (min_rmse_kbdm.py:33-41 over
+metrics.py:7-17) runs on the device (``llck_rmse_batched``): fused with the solve when the candidates are the ensemble's own
+line lists, one packed launch when they are given by the caller."""
 import logging
 
 import numpy as np
 
-from .metrics import calculate_freq_domain_rmse
-from .sampling import sample_kbdm
+from .ensemble import score_candidates
+from .sampling import sample_kbdm_scored
+from .sig_gen import _validate_parameters
 
 logger = logging.getLogger(__name__)
 
@@ -23,12 +26,14 @@ class MinRmseKbdmResult:
 
 def min_rmse_kbdm(data, dwell, m_range=None, l=None, samples=None):
     if samples is None:
-        samples, _ = sample_kbdm(data=data, dwell=dwell, m_range=m_range, l=l, q=0, p=1,
-                                 filter_invalid_features=True)          # min_rmse_kbdm.py:22-31
-    rmses = []
-    for i, line_list in enumerate(samples):
-        rmse = calculate_freq_domain_rmse(data=data, params_est=line_list, dwell=dwell) if len(line_list) > 0 else np.inf
-        rmses.append(rmse)
+        samples, _, rmses = sample_kbdm_scored(data=data, dwell=dwell, m_range=m_range, l=l, q=0, p=1,
+                                               filter_invalid_features=True)          # min_rmse_kbdm.py:22-31
+    else:
+        for line_list in samples:                 # the reference's multi_fid validates every row (sig_gen.py:140-169)
+            for row in line_list:
+                _validate_parameters(*row)
+        rmses = score_candidates(np.asarray(data).ravel(), dwell, samples, filter_rows=False)
+    for i, rmse in enumerate(rmses):
         logger.debug('RMSE for sample #%d: %f', i, rmse)
     if not rmses:
         return None

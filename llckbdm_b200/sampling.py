@@ -25,6 +25,14 @@ def sample_kbdm(data, dwell, m_range, p, l, q=0, filter_invalid_features=True):
     Returns (line_lists, infos) in m_range order; members whose (filtered) line list is empty are
     omitted, exactly as the reference does (sampling.py:67-70).
     """
+    line_lists, infos, _ = sample_kbdm_scored(data, dwell, m_range, p, l, q, filter_invalid_features, score_rmse=False)
+    return line_lists, infos
+
+
+def sample_kbdm_scored(data, dwell, m_range, p, l, q=0, filter_invalid_features=True, score_rmse=True):
+    """``sample_kbdm`` plus, per kept member, the frequency-domain RMSE of its filtered line list against ``data`` computed on
+    the device from the solver's output (what reference min_rmse_kbdm.py:33-41 computes in a CPU loop afterwards).
+    Returns (line_lists, infos, rmses)."""
     ms, ls = [], []
     for m in m_range:
         logger.info(f'Computing KBDM with m = {m}')
@@ -32,11 +40,11 @@ def sample_kbdm(data, dwell, m_range, p, l, q=0, filter_invalid_features=True):
         ms.append(mm)
         ls.append(ll_)
     if not ms:
-        return [], []
+        return [], [], []
     if q > 0:
         logger.debug('Using Tikhonov Regularization with q=%f', q)
-    res = solve_ensemble(np.asarray(data).ravel(), ms, ls, p, q, dwell)
-    line_lists, infos = [], []
+    res = solve_ensemble(np.asarray(data).ravel(), ms, ls, p, q, dwell, score_rmse=score_rmse and filter_invalid_features)
+    line_lists, infos, rmses = [], [], []
     for k, (mm, ll_) in enumerate(zip(ms, ls)):
         raise_for_status(int(res.status[k]), mm)
         line_list = np.ascontiguousarray(res.line_lists[k, :ll_, :])
@@ -45,4 +53,6 @@ def sample_kbdm(data, dwell, m_range, p, l, q=0, filter_invalid_features=True):
         if len(line_list) > 0:
             line_lists.append(line_list)
             infos.append(KbdmInfo(m=mm, l=ll_, p=p, q=q, singular_values=res.sing_vals[k, :mm].copy()))
-    return line_lists, infos
+            if res.rmse is not None:
+                rmses.append(float(res.rmse[k]))
+    return line_lists, infos, rmses

@@ -16,6 +16,8 @@ sys.path.insert(0, '/root/reference')
 from llckbdm.kbdm import kbdm  # noqa: E402
 from llckbdm.sampling import sample_kbdm  # noqa: E402
 from llckbdm import sig_gen  # noqa: E402
+from llckbdm.metrics import calculate_freq_domain_rmse  # noqa: E402
+from llckbdm.min_rmse_kbdm import min_rmse_kbdm  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, '..', 'tests', 'golden')
@@ -71,6 +73,12 @@ def main():
     np.savez_compressed(os.path.join(OUT, "sample_kbdm_noisy.npz"),
                         n=len(lls), **{f"ll{i}": x for i, x in enumerate(lls)},
                         **{f"sv{i}": inf.singular_values for i, inf in enumerate(infos)})
+    # frequency-domain RMSE scoring (metrics.py:7-17) and the min_rmse_kbdm selection (min_rmse_kbdm.py:21-56) on the noisy members
+    rm = [calculate_freq_domain_rmse(cn, ll, 5e-4) for ll in lls]
+    res = min_rmse_kbdm(cn, 5e-4, samples=lls)
+    rm_truth = calculate_freq_domain_rmse(cn, params, 5e-4)
+    np.savez_compressed(os.path.join(OUT, "rmse_noisy.npz"), rmses=np.array(rm), min_index=res.min_index, min_rmse=res.min_rmse,
+                        rmse_truth=rm_truth)
     print("done")
 
 

@@ -151,6 +151,22 @@ def multi_fid_oracle(t, params):
     return out
 
 
+def freq_domain_rmse_oracle(data, params_est, dwell):
+    """Reference ``metrics.py:7-17``: RMSE of the REAL parts of fft(data)/sqrt(N) and fft(model)/sqrt(N), the model being
+    ``multi_fid`` of the candidate line list on ``t = np.arange(0, N*dwell, dwell)`` (``sig_gen.py:8-24``)."""
+    N = len(data)
+    t = np.arange(0, N * dwell, dwell)
+    est = np.fft.fft(multi_fid_oracle(t, params_est)) / np.sqrt(N)
+    ref = np.fft.fft(np.asarray(data, dtype=complex)) / np.sqrt(N)
+    return float(np.sqrt(np.mean((ref.real - est.real) ** 2)))
+
+
+def min_rmse_oracle(data, dwell, samples):
+    """Reference ``min_rmse_kbdm.py:33-55``: (argmin index, rmse list); empty candidates score inf."""
+    rmses = [freq_domain_rmse_oracle(data, ll, dwell) if len(ll) > 0 else np.inf for ll in samples]
+    return int(np.argmin(rmses)), rmses
+
+
 def brain_sim(N=2048, sigma=1e-3, seed=0, dwell=5e-4, params=BRAIN_SIM_PARAMS):
     """brain_sim(N, sigma, seed) of SURVEY.md §8(d): the 16-component FID (+ seeded complex noise)."""
     t = np.linspace(0, dwell * N, N, endpoint=False)     # _tests/fixtures.py:18-20

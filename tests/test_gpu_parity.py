@@ -372,6 +372,49 @@ def test_mixed_batch_rank_deficient_member_falls_back_to_jacobi(cuda):
     assert np.allclose(est[:, 2], BRAIN_SIM_PARAMS[:, 2], atol=1e-6)
 
 
+def test_rmse_scoring_kernel_matches_oracle_and_reference_golden(cuda, golden_dir):
+    """llck_rmse_batched (Parseval form, no FFT) vs the oracle's fft-based restatement of metrics.py:7-17 and the values the real
+    reference produced (tests/golden/rmse_noisy.npz): ragged candidates, an empty one, on-the-fly row filter."""
+    from llckbdm_b200.ensemble import score_candidates
+    from oracle.kbdm_oracle import BRAIN_SIM_PARAMS, filter_samples_oracle, freq_domain_rmse_oracle
+    fid = np.load(os.path.join(golden_dir, "brain_sim_fid.npz"))
+    g = np.load(os.path.join(golden_dir, "sample_kbdm_noisy.npz"))
+    r = np.load(os.path.join(golden_dir, "rmse_noisy.npz"))
+    lls = [g[f"ll{i}"] for i in range(int(g["n"]))]
+    got = score_candidates(fid["noisy"], DWELL, lls + [BRAIN_SIM_PARAMS, np.zeros((0, 4))])
+    assert np.allclose(got[:len(lls)], r["rmses"], rtol=1e-9, atol=0)
+    assert abs(got[len(lls)] - float(r["rmse_truth"])) < 1e-9 * float(r["rmse_truth"])
+    assert got[-1] == np.inf
+    # unfiltered solver output + filter on the fly == oracle on the filtered list; odd N and N not a multiple of 256
+    rng = np.random.default_rng(5)
+    for N in (2048, 1000, 777):
+        data = fid["noisy"][:N]
+        cand = np.column_stack([rng.random(40) - 0.2, rng.random(40) * 0.2 - 0.02, rng.uniform(-900, 900, 40), rng.uniform(-3, 3, 40)])
+        cand[3, 1] = np.inf
+        want = freq_domain_rmse_oracle(data, filter_samples_oracle(cand), DWELL)
+        got = score_candidates(data, DWELL, [cand], filter_rows=True)[0]
+        assert abs(got - want) < 1e-10 * want, (N, got, want)
+
+
+def test_min_rmse_kbdm_fused_scoring_matches_oracle(cuda):
+    """min_rmse_kbdm(samples=None): members solved and scored on the device in one pass == oracle solve + oracle scoring."""
+    from llckbdm_b200.min_rmse_kbdm import min_rmse_kbdm
+    from oracle.kbdm_oracle import brain_sim, min_rmse_oracle, sample_kbdm_oracle
+    c = brain_sim(1024, 1e-3, 3)
+    m_range = [60, 100, 128, 200]
+    res = min_rmse_kbdm(c, DWELL, m_range=m_range, l=None)
+    lls, _ = sample_kbdm_oracle(c, DWELL, m_range, 1, None)
+    k, rmses = min_rmse_oracle(c, DWELL, lls)
+    assert res.min_index == k and len(res.rmses_list) == len(rmses)
+    assert np.allclose(res.rmses_list, rmses, rtol=1e-6)
+    assert np.allclose(res.min_rmse, rmses[k], rtol=1e-6)
+    # candidates given by the caller: same scores through the packed launch
+    res2 = min_rmse_kbdm(c, DWELL, samples=res.samples)
+    assert res2.min_index == k and np.allclose(res2.rmses_list, res.rmses_list, rtol=1e-12)
+    with pytest.raises(ValueError, match="T2 must be positive"):
+        min_rmse_kbdm(c, DWELL, samples=[np.array([[1.0, -1.0, 10.0, 0.0]])])
+
+
 def test_noiseless_rank_deficient_input_true_components(cuda):
     """Noiseless brain_sim (numerical rank 16, cond ~1e18): kernels must not NaN/hang; the 16 true components match the
     oracle (spurious poles are not reproducible between any two implementations)."""

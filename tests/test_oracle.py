@@ -112,3 +112,17 @@ def test_einsum_and_gemm_normalisation_agree():
 
 def test_flop_model():
     assert flops_per_solve(1024, 1024) == pytest.approx(193 * 1024 ** 3)
+
+
+def test_rmse_oracle_matches_reference_golden(golden_dir):
+    """freq_domain_rmse_oracle / min_rmse_oracle vs values produced by the real reference (metrics.py:7-17, min_rmse_kbdm.py:21-56)."""
+    from oracle.kbdm_oracle import BRAIN_SIM_PARAMS, freq_domain_rmse_oracle, min_rmse_oracle
+    fid = np.load(os.path.join(golden_dir, "brain_sim_fid.npz"))
+    g = np.load(os.path.join(golden_dir, "sample_kbdm_noisy.npz"))
+    r = np.load(os.path.join(golden_dir, "rmse_noisy.npz"))
+    lls = [g[f"ll{i}"] for i in range(int(g["n"]))]
+    k, rmses = min_rmse_oracle(fid["noisy"], 5e-4, lls)
+    assert np.allclose(rmses, r["rmses"], rtol=1e-10, atol=0)
+    assert k == int(r["min_index"]) and abs(rmses[k] - float(r["min_rmse"])) <= 1e-10 * float(r["min_rmse"])
+    assert abs(freq_domain_rmse_oracle(fid["noisy"], BRAIN_SIM_PARAMS, 5e-4) - float(r["rmse_truth"])) <= 1e-10 * float(r["rmse_truth"])
+    assert min_rmse_oracle(fid["noisy"], 5e-4, [np.zeros((0, 4)), lls[0]])[1][0] == np.inf
