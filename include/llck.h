@@ -104,6 +104,18 @@ int llck_bidiag_test(void* A, int32_t m, int32_t ld, double* d_out, double* e_ou
 int llck_rmse_batched(const void* data, int32_t N, double dwell, const double* line_lists, int64_t ll_stride,
                       const int32_t* n_rows, int32_t batch, int32_t filter, double amplitude_tol, double* rmse_out, void* stream);
 
+/* Silhouette coefficients of `nclusterings` labelings of the same n points -- replaces sklearn.metrics.silhouette_samples as
+ * called by llckbdm/llckbdm.py:291 on the 4-dimensional line-list features (llckbdm.py:202-230); Euclidean metric, every label
+ * value (HDBSCAN's noise label included) is a cluster, singleton clusters score 0.  Stream-ordered, asynchronous.
+ *   X           device float64 [n][4]
+ *   order       device int32 [nclusterings][n]    point indices sorted by label
+ *   seg         device int32 [nclusterings][n+1]  start offset of each cluster in `order` (nseg+1 entries used)
+ *   nseg        device int32 [nclusterings]       number of clusters
+ *   cluster_of  device int32 [nclusterings][n]    cluster index (0..nseg-1) of the point at each sorted position
+ *   out         device float64 [nclusterings][n]  silhouette of every point, indexed by ORIGINAL point index              */
+int llck_silhouette_batched(const double* X, int32_t n, const int32_t* order, const int32_t* seg, const int32_t* nseg,
+                            const int32_t* cluster_of, int32_t nclusterings, double* out, void* stream);
+
 /* Stage entry (tests): divide-and-conquer SVD of `batch` real upper-bidiagonal matrices (second half of the replacement of
  * scipy.linalg.svd, llckbdm/kbdm.py:166).  d, e: device [batch][ld] (diagonal m, super-diagonal m-1); m: host [batch];
  * ld multiple of 64.  Outputs (device): sing_vals [batch][ld] descending, Us = U*diag(s) and V as complex128 [batch][ld*ld]

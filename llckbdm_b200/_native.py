@@ -20,6 +20,7 @@ SYMBOLS = (
     "llck_bidiag_test",
     "llck_bdc_test",
     "llck_rmse_batched",
+    "llck_silhouette_batched",
 )
 
 FLAG_DEBUG_KEEP = 1
@@ -76,6 +77,8 @@ def load():
     lib.llck_bdc_test.argtypes = [c_vp, c_vp, ctypes.POINTER(c_int), c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.llck_rmse_batched.restype = c_int
     lib.llck_rmse_batched.argtypes = [c_vp, c_int, c_dbl, c_vp, c_i64, c_vp, c_int, c_int, c_dbl, c_vp, c_vp]
+    lib.llck_silhouette_batched.restype = c_int
+    lib.llck_silhouette_batched.argtypes = [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]
     _lib = lib
     return lib
 

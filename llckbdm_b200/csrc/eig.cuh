@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
 
     int ihi = n - 1, its = 0, nsweeps = 0;
     bool failed = false;
-    long long tp[6] = {0, 0, 0, 0, 0, 0};   // scan+shifts, window load, chase, store, strips, small blocks
+    long long tp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // scan+shifts, window load, chase, store, strips, small blocks, AED load, AED warp work, AED strips, AED calls
     long long tc = clock64();
 #define PROF(i) do { if (prof) { long long tn_ = clock64(); tp[i] += tn_ - tc; tc = tn_; } } while (0)
     while (ihi >= 0) {
@@ -750,11 +750,14 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 Ww[r + E_LDW * c] = mkc(r == c ? 1.0 : 0.0, 0.0);
             }
             __syncthreads();
+            PROF(6);
             if (warp == 0) {
                 int r = warp_aed(Hw, Ww, nw, spike, shifts, Hs, iscr + 33, Hs + 64);
                 if (lane == 0) iscr[32] = r;
             }
             __syncthreads();
+            PROF(7);
+            if (prof) ++tp[9];
             const int ns = iscr[32];
             if (ns < 0) { failed = true; break; }
             const int nd = nw - ns;
@@ -766,7 +769,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 if (tid == 0) Hb[kwtop + (long long)ld * (kwtop - 1)] = Hs[64];
                 apply_window_transform(Hb, Zb, ld, n, kwtop, ihi + 1, Ww, tiles, iscr + 40);
             }
-            PROF(5);
+            PROF(8);
             if (nd > 0) { ihi -= nd; its = 0; }
             if (nd * 100 > 14 * nw || ihi - ilo + 1 <= E_W) continue;     // good deflation: look again before sweeping
             if (ns < 2 || (its > 0 && its % 6 == 0)) {
@@ -864,7 +867,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
     if (tid == 0) {
         if (failed) atomicMax(&status[b], 1);
         if (sweeps_out) sweeps_out[b] = nsweeps;
-        if (prof) for (int i = 0; i < 6; ++i) prof[6 * b + i] = tp[i];
+        if (prof) for (int i = 0; i < 10; ++i) prof[10 * b + i] = tp[i];
     }
 #undef PROF
 }

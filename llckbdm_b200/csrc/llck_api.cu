@@ -16,6 +16,7 @@
 #include "svd_real.cuh"
 #include "bdc.cuh"
 #include "rmse.cuh"
+#include "silhouette.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -243,6 +244,15 @@ int llck_rmse_batched(const void* data, int32_t N, double dwell, const double* l
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaFuncSetAttribute(rmse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     rmse_kernel<<<batch, RMSE_THREADS, sm, st>>>((const cplx*)data, N, dwell, line_lists, ll_stride, n_rows, filter, amplitude_tol, rmse_out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int llck_silhouette_batched(const double* X, int32_t n, const int32_t* order, const int32_t* seg, const int32_t* nseg,
+                            const int32_t* cluster_of, int32_t nclusterings, double* out, void* stream) {
+    if (!X || !order || !seg || !nseg || !cluster_of || !out || n < 1 || nclusterings < 1 || nclusterings > 65535) return LLCK_E_BADARG;
+    dim3 grid((n + SIL_THREADS - 1) / SIL_THREADS, nclusterings);
+    silhouette_kernel<<<grid, SIL_THREADS, 0, (cudaStream_t)stream>>>(X, n, order, seg, nseg, cluster_of, out);
     CK(cudaGetLastError());
     return 0;
 }
@@ -748,26 +758,26 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         TICK();   // 5: hessenberg done
         CK(cudaFuncSetAttribute(hqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HQR_SMEM_BYTES));
         long long* d_prof = nullptr;
-        if (verbose) { CK(cudaMalloc(&d_prof, sizeof(long long) * 6 * batch)); }
+        if (verbose) { CK(cudaMalloc(&d_prof, sizeof(long long) * 10 * batch)); }
         int hqr_trains = 1;
         if (const char* ev = getenv("LLCK_HQR_TRAINS")) hqr_trains = atoi(ev) > 1 ? 2 : 1;
         hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains);
         CK(cudaGetLastError());
         if (verbose) {
-            long long* hp = (long long*)malloc(sizeof(long long) * 6 * batch);
-            CK(cudaMemcpyAsync(hp, d_prof, sizeof(long long) * 6 * batch, cudaMemcpyDeviceToHost, st));
+            long long* hp = (long long*)malloc(sizeof(long long) * 10 * batch);
+            CK(cudaMemcpyAsync(hp, d_prof, sizeof(long long) * 10 * batch, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            double tot[6] = {0, 0, 0, 0, 0, 0};
-            for (int b = 0; b < batch; ++b) for (int i = 0; i < 6; ++i) tot[i] += (double)hp[6 * b + i] / batch;
-            fprintf(stderr, "[llck] hqr phase Mcycles/member: scan+shifts=%.1f load=%.1f chase=%.1f store=%.1f strips=%.1f aed+small=%.1f\n",
-                    tot[0] / 1e6, tot[1] / 1e6, tot[2] / 1e6, tot[3] / 1e6, tot[4] / 1e6, tot[5] / 1e6);
-            double mn = 1e300, mx = 0, mxa = 0, mxs = 0; int imx = 0;
+            double tot[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int b = 0; b < batch; ++b) for (int i = 0; i < 10; ++i) tot[i] += (double)hp[10 * b + i] / batch;
+            fprintf(stderr, "[llck] hqr phase Mcycles/member: scan+shifts=%.1f load=%.1f chase=%.1f store=%.1f strips=%.1f small=%.1f | AED: load=%.1f warp=%.1f strips=%.1f calls=%.0f\n",
+                    tot[0] / 1e6, tot[1] / 1e6, tot[2] / 1e6, tot[3] / 1e6, tot[4] / 1e6, tot[5] / 1e6, tot[6] / 1e6, tot[7] / 1e6, tot[8] / 1e6, tot[9]);
+            double mn = 1e300, mx = 0;
             for (int b = 0; b < batch; ++b) {
-                double t = 0; for (int i = 0; i < 6; ++i) t += (double)hp[6 * b + i];
+                double t = 0; for (int i = 0; i < 9; ++i) t += (double)hp[10 * b + i];
                 if (t < mn) mn = t;
-                if (t > mx) { mx = t; imx = b; mxa = (double)hp[6 * b + 5]; mxs = (double)hp[6 * b + 4]; }
+                if (t > mx) mx = t;
             }
-            fprintf(stderr, "[llck] hqr per-member total Mcycles: min=%.1f max=%.1f (member %d: aed+small=%.1f strips=%.1f)\n", mn / 1e6, mx / 1e6, imx, mxa / 1e6, mxs / 1e6);
+            fprintf(stderr, "[llck] hqr per-member total Mcycles: min=%.1f max=%.1f\n", mn / 1e6, mx / 1e6);
             free(hp); cudaFree(d_prof);
 
         }

@@ -147,6 +147,48 @@ def score_candidates(data, dwell, candidates, filter_rows=False, device=None):
         return [float(x) for x in out.cpu().numpy()]
 
 
+def silhouette_samples_device(features, labelings, device=None):
+    """Silhouette coefficient of every point for each labeling of the same points, on the device (llck_silhouette_batched;
+    replaces sklearn.metrics.silhouette_samples as called at reference llckbdm.py:291).
+
+    features: float64 [n, 4]; labelings: list of int arrays [n] (every label value, including -1, is a cluster, as in sklearn).
+    Returns float64 [len(labelings), n]."""
+    torch = _require_cuda()
+    lib = _native.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    X = np.ascontiguousarray(features, dtype=np.float64)
+    n = X.shape[0]
+    if X.ndim != 2 or X.shape[1] != 4:
+        raise ValueError("features must be [n, 4]")
+    C = len(labelings)
+    if C == 0 or n == 0:
+        return np.zeros((C, n))
+    order = np.empty((C, n), dtype=np.int32)
+    seg = np.zeros((C, n + 1), dtype=np.int32)
+    nseg = np.empty(C, dtype=np.int32)
+    cluster_of = np.empty((C, n), dtype=np.int32)
+    for c, labels in enumerate(labelings):
+        uniq, inv = np.unique(np.asarray(labels), return_inverse=True)
+        o = np.argsort(inv, kind="stable")
+        order[c] = o
+        cluster_of[c] = inv[o]
+        nseg[c] = len(uniq)
+        seg[c, 1:len(uniq) + 1] = np.cumsum(np.bincount(inv, minlength=len(uniq)))
+    out = np.empty((C, n))
+    with torch.cuda.device(dev):
+        Xd = torch.from_numpy(X).to(dev)
+        chunk = 256                                        # clusterings per launch (bounds the device buffers)
+        for c0 in range(0, C, chunk):
+            c1 = min(C, c0 + chunk)
+            od, sd, nd, cd = (torch.from_numpy(a[c0:c1].copy()).to(dev) for a in (order, seg, nseg, cluster_of))
+            res = torch.empty((c1 - c0, n), dtype=torch.float64, device=dev)
+            rc = lib.llck_silhouette_batched(Xd.data_ptr(), n, od.data_ptr(), sd.data_ptr(), nd.data_ptr(), cd.data_ptr(),
+                                             c1 - c0, res.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _native.check_rc(rc, "llck_silhouette_batched")
+            out[c0:c1] = res.cpu().numpy()
+    return out
+
+
 def flatten_signals(signals, M):
     """One shared 1-D FID, or a list of M FIDs -> (flat complex128 array, int64 offsets)."""
     if isinstance(signals, np.ndarray) and signals.ndim == 1:

@@ -1,22 +1,25 @@
 """Drop-in for reference llckbdm/llckbdm.py (LLC-KBDM driver).
 
 The ensemble of KBDM solves (79 % of the reference's wall time) runs on the GPU
-through ``sampling.sample_kbdm``; pooling, HDBSCAN clustering, cluster averaging and the min-RMSE
-selection stay on the host exactly as in the reference (llckbdm.py:94-141) -- they are the "next"
-rows of the scope table, not part of this hot path.
+through ``sampling.sample_kbdm``.  Of the clustering stage ("next" row f-1 of the scope table) the two O(n^2)/O(M n K) loops
+are on the GPU too: the silhouette coefficients of all clusterings (one batched ``llck_silhouette_batched`` launch instead of
+M-1 ``sklearn.metrics.silhouette_samples`` calls, llckbdm.py:291) and the min-RMSE scoring of the cluster averages
+(``llck_rmse_batched``, llckbdm.py:120).  The HDBSCAN fits themselves stay on the host (third-party algorithm; label-for-label
+agreement is kept by calling the same clusterer) but run in parallel processes; pooling and cluster averaging are host numpy.
 
 Clusterer: the reference imports the un-vendored ``hdbscan`` package (llckbdm.py:3).  If it is
 importable it is used; otherwise ``sklearn.cluster.HDBSCAN`` with the same defaults
 (min_cluster_size=5, euclidean, EOM, allow_single_cluster=False) stands in.
 """
 import logging
+import os
 
 import numpy as np
-from sklearn.metrics import silhouette_samples
 
 from .metrics import calculate_freq_domain_rmse
 from .min_rmse_kbdm import min_rmse_kbdm
 from .sampling import filter_samples, sample_kbdm
+from .ensemble import silhouette_samples_device
 from .sig_gen import gen_t_freq_arrays, multi_fid
 
 logger = logging.getLogger(__name__)
@@ -65,12 +68,10 @@ def llc_kbdm(data, dwell, m_range, p=1, l=None, q=0.0):
     samples = filter_samples(np.concatenate(line_lists))
     features = _transform_line_lists(samples, dwell)
     n_members = len(m_range)
-    results = []
-    for min_samples in range(1, n_members):
-        logger.debug('HDBSCAN with min_samples = %d', min_samples)
-        res = _cluster_line_lists(samples=samples, transformed_samples=features, min_samples=min_samples)
-        if res.num_clusters > 0:
-            results.append(res)
+    # HDBSCAN for min_samples = 1..M-1 (reference llckbdm.py:104-116): the fits are independent -> spread over the host cores;
+    # the silhouettes of all clusterings are then ONE batched device launch instead of M-1 O(n^2) sklearn calls.
+    labelings = _fit_all(features, list(range(1, n_members)))
+    results = _results_from_labelings(samples, features, labelings)
     best = min_rmse_kbdm(data=data, dwell=dwell, samples=[r.summarized_line_list for r in results])
     if best is None:
         return LlcKbdmResult()
@@ -127,24 +128,49 @@ def _inverse_transform_line_lists(transformed_line_lists, dwell):
                             transformed_line_lists[:, 3]))
 
 
+def _fit_one(features, min_samples):
+    model = _HDBSCAN(min_samples=min_samples)
+    model.fit(features)
+    return np.asarray(model.labels_)
+
+
+def _fit_all(features, min_samples_list):
+    """Labels of one HDBSCAN fit per min_samples value, in order.  Fits run in parallel host processes when there are enough
+    of them to pay for the process start-up (LLCK_CLUSTER_JOBS overrides the worker count; 1 = serial)."""
+    n_fits = len(min_samples_list)
+    jobs = int(os.environ.get("LLCK_CLUSTER_JOBS", "0")) or min(n_fits, os.cpu_count() or 1)
+    if jobs <= 1 or n_fits < 8 or len(features) < 4000:
+        return [_fit_one(features, ms) for ms in min_samples_list]
+    from joblib import Parallel, delayed
+    return Parallel(n_jobs=jobs, prefer="processes")(delayed(_fit_one)(features, ms) for ms in min_samples_list)
+
+
+def _results_from_labelings(samples, features, labelings):
+    """ClusteringResult per labeling with >= 1 cluster (reference llckbdm.py:285-321), silhouettes from one device launch."""
+    keep = [lab for lab in labelings if len(set(lab.tolist()) - {-1}) > 0]
+    if not keep:
+        return []
+    sil_all = silhouette_samples_device(features, keep)
+    results = []
+    for labels, sil in zip(keep, sil_all):
+        num_clusters = len(set(labels.tolist()) - {-1})
+        clustered, cluster_sil = [], []
+        for lab in range(num_clusters):
+            members = np.nonzero(labels == lab)
+            clustered.append(members)
+            cluster_sil.append(np.average(sil[members]))
+        results.append(ClusteringResult(num_clusters=num_clusters, labels=labels, clustered=clustered,
+                                        non_clustered=np.nonzero(labels == -1),
+                                        summarized_line_list=_summarize_clusters(samples=samples, clusters=clustered),
+                                        clustered_silhouettes=np.array(cluster_sil)))
+    return results
+
+
 def _cluster_line_lists(samples, transformed_samples, min_samples):
     """One HDBSCAN fit + per-cluster mean silhouette + cluster averages (reference llckbdm.py:264-321)."""
-    model = _HDBSCAN(min_samples=min_samples)
-    model.fit(transformed_samples)
-    labels = model.labels_
-    num_clusters = len(set(labels) - {-1})
-    if num_clusters == 0:
-        return ClusteringResult(num_clusters=0, labels=labels)
-    sil = silhouette_samples(transformed_samples, labels)
-    clustered, cluster_sil = [], []
-    for lab in range(num_clusters):
-        members = np.nonzero(labels == lab)
-        clustered.append(members)
-        cluster_sil.append(np.average(sil[members]))
-    return ClusteringResult(num_clusters=num_clusters, labels=labels, clustered=clustered,
-                            non_clustered=np.nonzero(labels == -1),
-                            summarized_line_list=_summarize_clusters(samples=samples, clusters=clustered),
-                            clustered_silhouettes=np.array(cluster_sil))
+    labels = _fit_one(transformed_samples, min_samples)
+    res = _results_from_labelings(samples, transformed_samples, [labels])
+    return res[0] if res else ClusteringResult(num_clusters=0, labels=labels)
 
 
 def _summarize_clusters(samples, clusters, summarizer=np.average):

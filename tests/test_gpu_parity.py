@@ -171,6 +171,60 @@ def test_llc_kbdm_cluster_parity_noisy(cuda):
     assert np.allclose(a[:, 1], b[:, 1], rtol=1e-6)
 
 
+def test_silhouette_kernel_matches_sklearn(cuda):
+    """llck_silhouette_batched vs sklearn.metrics.silhouette_samples (the call at reference llckbdm.py:291): several labelings of
+    the same points in one launch, noise label -1 as a cluster, singleton clusters, many tiny clusters, one big cluster.
+    sklearn's Euclidean distances use the |x|^2+|y|^2-2xy expansion (absolute error ~1e-8 on near-coincident points), the
+    kernel takes differences directly, hence the 1e-6 absolute tolerance on coefficients in [-1, 1]."""
+    from sklearn.metrics import silhouette_samples
+    from llckbdm_b200.ensemble import silhouette_samples_device
+    rng = np.random.default_rng(2)
+    cent = rng.uniform(-1, 1, (40, 3))
+    X = np.concatenate([np.repeat(cent, 12, axis=0) + 1e-3 * rng.standard_normal((480, 3)), rng.uniform(-1, 1, (777, 3))])
+    X = np.column_stack([X, np.zeros(len(X))])
+    n = len(X)
+    lab_a = np.concatenate([np.repeat(np.arange(40), 12), -np.ones(777, dtype=int)])
+    lab_b = rng.integers(-1, 5, n)
+    lab_c = np.arange(n) // 3                      # tiny clusters
+    lab_c[-1] = 10 ** 6                            # a singleton
+    lab_d = (X[:, 0] > 0).astype(int)
+    labelings = [lab_a, lab_b, lab_c, lab_d]
+    got = silhouette_samples_device(X, labelings)
+    for lab, g in zip(labelings, got):
+        want = silhouette_samples(X, lab)
+        assert np.abs(g - want).max() < 1e-6, np.abs(g - want).max()
+    assert got[2][-1] == 0.0
+
+
+def test_llc_kbdm_matches_host_clustering_stage(cuda):
+    """llc_kbdm end to end (GPU solves, parallel fits, device silhouettes, device RMSE selection) == the same line lists pushed
+    through a literal host restatement of reference llckbdm.py:93-141 (same clusterer, sklearn silhouettes, oracle RMSE)."""
+    from sklearn.metrics import silhouette_samples
+    from llckbdm_b200 import llckbdm as L
+    from llckbdm_b200.sampling import filter_samples, sample_kbdm
+    from oracle.kbdm_oracle import brain_sim, min_rmse_oracle
+    c = brain_sim(1024, 1e-3, 5)
+    m_range = list(range(100, 112))
+    res = L.llc_kbdm(c, DWELL, m_range)
+    lls, _ = sample_kbdm(c, DWELL, m_range, p=1, l=None)
+    samples = filter_samples(np.concatenate(lls))
+    feats = L._transform_line_lists(samples, DWELL)
+    cands, sils = [], []
+    for ms in range(1, len(m_range)):
+        labels = L._fit_one(feats, ms)
+        nc = len(set(labels.tolist()) - {-1})
+        if nc == 0:
+            continue
+        sv = silhouette_samples(feats, labels)
+        clusters = [np.nonzero(labels == k) for k in range(nc)]
+        cands.append(L._summarize_clusters(samples, clusters))
+        sils.append(np.array([np.average(sv[cl]) for cl in clusters]))
+    k, rmses = min_rmse_oracle(c, DWELL, cands)
+    assert np.allclose(res.line_list, cands[k], rtol=1e-12, atol=0)
+    assert abs(res.rmse - rmses[k]) < 1e-9 * rmses[k]
+    assert np.abs(res.silhouette - sils[k]).max() < 1e-6
+
+
 def test_singular_member_raises_linalgerror(cuda):
     """Exact zero singular value among the kept ones -> LinAlgError (np.linalg.inv behaviour at kbdm.py:186)."""
     from llckbdm_b200.kbdm import kbdm
