@@ -13,7 +13,8 @@
 #define E_NWARPS 16
 #define E_W 64          // window size
 #define E_NB 16         // shifts (bulges) per multishift sweep
-#define E_LDW 68        // ld of Hw/Ww in smem (= 4 mod 8)
+#define E_LDW 68        // ld of Ww in smem (= 4 mod 8: conflict-free DMMA fragment reads)
+#define E_LDH 65        // ld of Hw in smem (odd: row rotations, one lane per COLUMN, hit 8 distinct 16-byte bank groups)
 #define E_MAT (E_LDW * E_W)
 #define E_TILE (68 * 32)   // strip tile: [68 x 32] (row strips) or [34 x 64] (col strips)
 #define E_LDS 17        // ld of the shift scratch matrix
@@ -375,6 +376,15 @@ __device__ __noinline__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, 
             double c; cplx s;
             givens(x, y, c, s);
             const cplx cs = cconj(s);
+            // the accumulated transform only depends on (c, s) and on this lane's own rows: issue it first so that its
+            // shared-memory latency overlaps the dependent row / column rotations of the window
+            if (W != nullptr) {
+                for (int row = lane; row < wrows; row += 32) {
+                    cplx a = W[row + ldw * k], bq = W[row + ldw * (k + 1)];
+                    W[row + ldw * k] = cadd(cscale(a, c), cmul(cs, bq));
+                    W[row + ldw * (k + 1)] = csub(cscale(bq, c), cmul(s, a));
+                }
+            }
             __syncwarp();
             const int c0 = (k > ilo) ? k - 1 : k;
             for (int col = c0 + lane; col < n; col += 32) {
@@ -389,13 +399,6 @@ __device__ __noinline__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, 
                 cplx a = Hs[row + ldh * k], bq = Hs[row + ldh * (k + 1)];
                 Hs[row + ldh * k] = cadd(cscale(a, c), cmul(cs, bq));
                 Hs[row + ldh * (k + 1)] = csub(cscale(bq, c), cmul(s, a));
-            }
-            if (W != nullptr) {
-                for (int row = lane; row < wrows; row += 32) {
-                    cplx a = W[row + ldw * k], bq = W[row + ldw * (k + 1)];
-                    W[row + ldw * k] = cadd(cscale(a, c), cmul(cs, bq));
-                    W[row + ldw * (k + 1)] = csub(cscale(bq, c), cmul(s, a));
-                }
             }
             __syncwarp();
         }
@@ -413,11 +416,11 @@ __device__ __noinline__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, 
 //      ns x ns block to Hessenberg form (transformations accumulated in V); the caller writes T back and applies V.
 // Returns ns (>= 0), or -1 if the window QR failed.  out[0] = 1 if T/V must be written back.  newsub = new H[kwtop,kwtop-1].
 // ---------------------------------------------------------------------------------------------
-#define E_NW 32
+#define E_NW 24        // AED window (measured at m=1024: 16 -> 1280, 24 -> 1135, 32 -> 1188, 40 -> 1397 Mcycles per member)
 __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shifts, cplx* vbuf, int* out, cplx* newsub) {
     const int lane = threadIdx.x & 31;
-    const int L = E_LDW;
-    if (warp_small_hqr(T, L, V, L, nw, nw) < 0) return -1;
+    const int L = E_LDH, LV = E_LDW;       // T lives in Hw (ld E_LDH), V in Ww (ld E_LDW)
+    if (warp_small_hqr(T, L, V, LV, nw, nw) < 0) return -1;
     __syncwarp();
     int ns = nw, ilst = 0;
     const double s1 = cabs1(s);
@@ -426,7 +429,7 @@ __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shi
         if (ilst >= ns) break;
         double foo = cabs1(T[(ns - 1) + L * (ns - 1)]);
         if (foo == 0.0) foo = s1;
-        if (s1 * cabs1(V[0 + L * (ns - 1)]) <= fmax(smallnum, LLCK_EPS * foo)) {
+        if (s1 * cabs1(V[0 + LV * (ns - 1)]) <= fmax(smallnum, LLCK_EPS * foo)) {
             --ns;
         } else {
             // move T[ns-1,ns-1] up to position ilst by adjacent swaps
@@ -447,9 +450,9 @@ __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shi
                     T[row + L * (k + 1)] = csub(cscale(bq, c), cmul(sn, a));
                 }
                 for (int row = lane; row < nw; row += 32) {
-                    cplx a = V[row + L * k], bq = V[row + L * (k + 1)];
-                    V[row + L * k] = cadd(cscale(a, c), cmul(csn, bq));
-                    V[row + L * (k + 1)] = csub(cscale(bq, c), cmul(sn, a));
+                    cplx a = V[row + LV * k], bq = V[row + LV * (k + 1)];
+                    V[row + LV * k] = cadd(cscale(a, c), cmul(csn, bq));
+                    V[row + LV * (k + 1)] = csub(cscale(bq, c), cmul(sn, a));
                 }
                 __syncwarp();
                 if (lane == 0) { T[k + L * k] = t22; T[(k + 1) + L * (k + 1)] = t11; }
@@ -469,7 +472,7 @@ __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shi
         // ---- reflect the spike w = s * conj(V[0, 0:ns]) to beta * e1 ----
         double part = 0.0;
         for (int j = lane; j < ns; j += 32) {
-            cplx w = cmul(s, cconj(V[0 + L * j]));
+            cplx w = cmul(s, cconj(V[0 + LV * j]));
             vbuf[j] = w;
             if (j > 0) part += cabs2(w);
         }
@@ -498,9 +501,9 @@ __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shi
             }
             for (int row = lane; row < nw; row += 32) {           // V[:, 0:ns] <- V P
                 cplx y = mkc(0.0, 0.0);
-                for (int j = 0; j < ns; ++j) y = cfma(V[row + L * j], vbuf[j], y);
+                for (int j = 0; j < ns; ++j) y = cfma(V[row + LV * j], vbuf[j], y);
                 const cplx f = cmul(tau, y);
-                for (int j = 0; j < ns; ++j) V[row + L * j] = csub(V[row + L * j], cmul(f, cconj(vbuf[j])));
+                for (int j = 0; j < ns; ++j) V[row + LV * j] = csub(V[row + LV * j], cmul(f, cconj(vbuf[j])));
             }
             __syncwarp();
         }
@@ -536,9 +539,9 @@ __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shi
             }
             for (int row = lane; row < nw; row += 32) {           // right on V
                 cplx y = mkc(0.0, 0.0);
-                for (int i = 0; i < len; ++i) y = cfma(V[row + L * (k + 1 + i)], vbuf[i], y);
+                for (int i = 0; i < len; ++i) y = cfma(V[row + LV * (k + 1 + i)], vbuf[i], y);
                 const cplx f = cmul(tau, y);
-                for (int i = 0; i < len; ++i) V[row + L * (k + 1 + i)] = csub(V[row + L * (k + 1 + i)], cmul(f, cconj(vbuf[i])));
+                for (int i = 0; i < len; ++i) V[row + LV * (k + 1 + i)] = csub(V[row + LV * (k + 1 + i)], cmul(f, cconj(vbuf[i])));
             }
             __syncwarp();
         }
@@ -679,7 +682,7 @@ __device__ __forceinline__ int block_max_int(int v, int* scratch) {
 }
 
 // status: 0 ok, 1 = QR did not converge
-__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out, long long* prof, int max_trains) {
+__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out, long long* prof, int max_trains, int aed_nw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* Hw = reinterpret_cast<cplx*>(smem_raw);
     cplx* Ww = Hw + E_MAT;
@@ -714,12 +717,12 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 int r = idx & 63, c = idx >> 6;
                 cplx hv = mkc(0.0, 0.0);
                 if (r < size && c < size) hv = Hb[(ilo + r) + (long long)ld * (ilo + c)];
-                Hw[r + E_LDW * c] = hv;
+                Hw[r + E_LDH * c] = hv;
                 Ww[r + E_LDW * c] = mkc(r == c ? 1.0 : 0.0, 0.0);
             }
             __syncthreads();
             if (warp == 0) {
-                int r = warp_small_hqr(Hw, E_LDW, Ww, E_LDW, size, size);
+                int r = warp_small_hqr(Hw, E_LDH, Ww, E_LDW, size, size);
                 if (lane == 0) iscr[32] = r;
             }
             __syncthreads();
@@ -727,7 +730,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             PROF(5);
             for (int idx = tid; idx < size * size; idx += E_THREADS) {
                 int r = idx % size, c = idx / size;
-                Hb[(ilo + r) + (long long)ld * (ilo + c)] = Hw[r + E_LDW * c];
+                Hb[(ilo + r) + (long long)ld * (ilo + c)] = Hw[r + E_LDH * c];
             }
             apply_window_transform(Hb, Zb, ld, n, ilo, ihi + 1, Ww, tiles, iscr + 40);
             PROF(4);
@@ -739,14 +742,14 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
         // ---- aggressive early deflation on the trailing E_NW x E_NW window; its undeflated eigenvalues are the shifts ----
         int nbu = E_NB, ntrains = 1, ns_all = E_NB;
         {
-            const int nw = E_NW;                      // size > E_W >= E_NW
+            const int nw = aed_nw;                    // size > E_W >= nw
             const int kwtop = ihi - nw + 1;
             const cplx spike = Hb[kwtop + (long long)ld * (kwtop - 1)];
             for (int idx = tid; idx < E_W * E_W; idx += E_THREADS) {
                 int r = idx & 63, c = idx >> 6;
                 cplx hv = mkc(0.0, 0.0);
                 if (r < nw && c < nw && r <= c + 1) hv = Hb[(kwtop + r) + (long long)ld * (kwtop + c)];
-                Hw[r + E_LDW * c] = hv;
+                Hw[r + E_LDH * c] = hv;
                 Ww[r + E_LDW * c] = mkc(r == c ? 1.0 : 0.0, 0.0);
             }
             __syncthreads();
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             if (iscr[33]) {
                 for (int idx = tid; idx < nw * nw; idx += E_THREADS) {
                     int r = idx % nw, c = idx / nw;
-                    Hb[(kwtop + r) + (long long)ld * (kwtop + c)] = (r <= c + 1) ? Hw[r + E_LDW * c] : mkc(0.0, 0.0);
+                    Hb[(kwtop + r) + (long long)ld * (kwtop + c)] = (r <= c + 1) ? Hw[r + E_LDH * c] : mkc(0.0, 0.0);
                 }
                 if (tid == 0) Hb[kwtop + (long long)ld * (kwtop - 1)] = Hs[64];
                 apply_window_transform(Hb, Zb, ld, n, kwtop, ihi + 1, Ww, tiles, iscr + 40);
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 int r = idx & 63, c = idx >> 6;
                 cplx hv = mkc(0.0, 0.0);
                 if (r < ww && c < ww) hv = Hb[(ws + r) + (long long)ld * (ws + c)];
-                Hw[r + E_LDW * c] = hv;
+                Hw[r + E_LDH * c] = hv;
                 Ww[r + E_LDW * c] = mkc(r == c ? 1.0 : 0.0, 0.0);
             }
             __syncthreads();
@@ -819,20 +822,20 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 double c = 1.0; cplx s = mkc(0.0, 0.0);
                 if (active) {
                     cplx x, y;
-                    if (p == ilo - 1) { x = csub(Hw[(ilo - ws) + E_LDW * (ilo - ws)], tshifts[warp]); y = Hw[(ilo + 1 - ws) + E_LDW * (ilo - ws)]; }
-                    else { x = Hw[(p + 1 - ws) + E_LDW * (p - ws)]; y = Hw[(p + 2 - ws) + E_LDW * (p - ws)]; }
+                    if (p == ilo - 1) { x = csub(Hw[(ilo - ws) + E_LDH * (ilo - ws)], tshifts[warp]); y = Hw[(ilo + 1 - ws) + E_LDH * (ilo - ws)]; }
+                    else { x = Hw[(p + 1 - ws) + E_LDH * (p - ws)]; y = Hw[(p + 2 - ws) + E_LDH * (p - ws)]; }
                     givens(x, y, c, s);
                     const cplx cs = cconj(s);
                     const int r = p + 1 - ws;
                     const int c0 = max(p - ws, 0);
                     __syncwarp();
                     for (int col = c0 + lane; col < ww; col += 32) {
-                        cplx a = Hw[r + E_LDW * col], bq = Hw[(r + 1) + E_LDW * col];
-                        Hw[r + E_LDW * col] = cadd(cscale(a, c), cmul(s, bq));
-                        Hw[(r + 1) + E_LDW * col] = csub(cscale(bq, c), cmul(cs, a));
+                        cplx a = Hw[r + E_LDH * col], bq = Hw[(r + 1) + E_LDH * col];
+                        Hw[r + E_LDH * col] = cadd(cscale(a, c), cmul(s, bq));
+                        Hw[(r + 1) + E_LDH * col] = csub(cscale(bq, c), cmul(cs, a));
                     }
                     __syncwarp();
-                    if (p >= ilo && lane == 0) Hw[(r + 1) + E_LDW * (p - ws)] = mkc(0.0, 0.0);
+                    if (p >= ilo && lane == 0) Hw[(r + 1) + E_LDH * (p - ws)] = mkc(0.0, 0.0);
                 }
                 __syncthreads();
                 if (active) {
@@ -840,9 +843,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                     const int k = p + 1 - ws;
                     const int r1 = min(p + 3, ihi) - ws + 1;
                     for (int row = lane; row < r1; row += 32) {
-                        cplx a = Hw[row + E_LDW * k], bq = Hw[row + E_LDW * (k + 1)];
-                        Hw[row + E_LDW * k] = cadd(cscale(a, c), cmul(cs, bq));
-                        Hw[row + E_LDW * (k + 1)] = csub(cscale(bq, c), cmul(s, a));
+                        cplx a = Hw[row + E_LDH * k], bq = Hw[row + E_LDH * (k + 1)];
+                        Hw[row + E_LDH * k] = cadd(cscale(a, c), cmul(cs, bq));
+                        Hw[row + E_LDH * (k + 1)] = csub(cscale(bq, c), cmul(s, a));
                     }
                     for (int row = lane; row < ww; row += 32) {
                         cplx a = Ww[row + E_LDW * k], bq = Ww[row + E_LDW * (k + 1)];
@@ -855,7 +858,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             PROF(2);
             for (int idx = tid; idx < ww * ww; idx += E_THREADS) {
                 int r = idx % ww, c = idx / ww;
-                Hb[(ws + r) + (long long)ld * (ws + c)] = Hw[r + E_LDW * c];
+                Hb[(ws + r) + (long long)ld * (ws + c)] = Hw[r + E_LDH * c];
             }
             PROF(3);
             apply_window_transform(Hb, Zb, ld, n, ws, we, Ww, tiles, iscr + 40);
