@@ -682,7 +682,7 @@ __device__ __forceinline__ int block_max_int(int v, int* scratch) {
 }
 
 // status: 0 ok, 1 = QR did not converge
-__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out, long long* prof, int max_trains, int aed_nw) {
+__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out, long long* prof, int max_trains, int aed_nw, int nibble) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* Hw = reinterpret_cast<cplx*>(smem_raw);
     cplx* Ww = Hw + E_MAT;
@@ -774,7 +774,11 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             }
             PROF(8);
             if (nd > 0) { ihi -= nd; its = 0; }
-            if (nd * 100 > 14 * nw || ihi - ilo + 1 <= E_W) continue;     // good deflation: look again before sweeping
+            // good deflation: look again before sweeping.  A sweep costs O(n^2), the single-warp AED a constant, so the threshold
+            // (LAPACK's NIBBLE) grows for small matrices: measured hqr ms at nibble 14/30/60: n=1024 586/583/746, n=512 1024/972/918,
+            // n=256 635/585/504
+            const int nib = nibble > 0 ? nibble : (n > 768 ? 30 : 60);
+            if (nd * 100 > nib * nw || ihi - ilo + 1 <= E_W) continue;
             if (ns < 2 || (its > 0 && its % 6 == 0)) {
                 __syncthreads();
                 if (tid < E_NB) {

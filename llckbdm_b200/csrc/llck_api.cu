@@ -761,9 +761,10 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         if (verbose) { CK(cudaMalloc(&d_prof, sizeof(long long) * 10 * batch)); }
         int hqr_trains = 1;
         if (const char* ev = getenv("LLCK_HQR_TRAINS")) hqr_trains = atoi(ev) > 1 ? 2 : 1;
-        int aed_nw = E_NW;
+        int aed_nw = E_NW, nibble = 0;      // 0: adaptive
+        if (const char* ev = getenv("LLCK_AED_NIBBLE")) { int v = atoi(ev); if (v >= 1 && v <= 1000) nibble = v; }
         if (const char* ev = getenv("LLCK_AED_NW")) { int v = atoi(ev); if (v >= 8 && v <= 48) aed_nw = v; }
-        hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains, aed_nw);
+        hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains, aed_nw, nibble);
         CK(cudaGetLastError());
         if (verbose) {
             long long* hp = (long long*)malloc(sizeof(long long) * 10 * batch);
