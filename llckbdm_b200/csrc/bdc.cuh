@@ -20,7 +20,7 @@
 #pragma once
 #include "common.cuh"
 
-#define BDC_LEAF 64
+#define BDC_LEAF 32
 #define BDC_FALLBACK_RATIO 1e-8
 
 struct BdcParams {
