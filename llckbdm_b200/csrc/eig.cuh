@@ -556,7 +556,20 @@ __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shi
 //   H[ws:we, we:n] <- Ww^H H[ws:we, we:n];  H[0:ws, ws:we] <- H[0:ws, ws:we] Ww;  Z[:, ws:we] <- Z[:, ws:we] Ww
 // all E_THREADS threads participate; tiles: 2 x E_TILE double buffer
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, int n, int ws, int we, const cplx* Ww, cplx* tiles, int* kr) {
+// cluster-wide barrier with release/acquire ordering of the global-memory strip writes (no-op for a single CTA per member)
+__device__ __forceinline__ void hqr_cluster_sync(int csize) {
+    if (csize > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+}
+
+// With csize > 1 CTAs per member (small batches), every CTA of the cluster runs the same window computation redundantly (identical
+// Ww in its own shared memory) and applies it to every csize-th strip tile only; the call ends with a cluster barrier.
+__device__ __noinline__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, int n, int ws, int we, const cplx* Ww, cplx* tiles, int* kr,
+                                                    int crank, int csize) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int ww = we - ws;
     // W is a product of plane rotations: every column has a limited range of nonzero rows.  kr[2J], kr[2J+1] = first/last+1
@@ -597,10 +610,10 @@ __device__ __noinline__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, 
             cp_async_commit();
         };
         const int wr = warp >> 1, wc = warp & 1;
-        if (ntiles > 0) load(0, 0);
-        for (int tl = 0; tl < ntiles; ++tl) {
-            const int buf = tl & 1;
-            if (tl + 1 < ntiles) { load(buf ^ 1, tl + 1); cp_async_wait<1>(); }
+        if (crank < ntiles) load(0, crank);
+        for (int tl = crank, it = 0; tl < ntiles; tl += csize, ++it) {
+            const int buf = it & 1;
+            if (tl + csize < ntiles) { load(buf ^ 1, tl + csize); cp_async_wait<1>(); }
             else cp_async_wait<0>();
             __syncthreads();
             const cplx* T = tiles + buf * E_TILE;
@@ -643,10 +656,10 @@ __device__ __noinline__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, 
         // warps w, w+4, w+8, w+12 share one SM sub-partition (and its DMMA pipe): give each sub-partition all four column
         // groups (their k-ranges differ) so that the four pipes carry equal work
         const int wr = warp >> 2, wc = (warp + (warp >> 2)) & 3;
-        if (ntiles > 0) load(0, 0);
-        for (int tl = 0; tl < ntiles; ++tl) {
-            const int buf = tl & 1;
-            if (tl + 1 < ntiles) { load(buf ^ 1, tl + 1); cp_async_wait<1>(); }
+        if (crank < ntiles) load(0, crank);
+        for (int tl = crank, it = 0; tl < ntiles; tl += csize, ++it) {
+            const int buf = it & 1;
+            if (tl + csize < ntiles) { load(buf ^ 1, tl + csize); cp_async_wait<1>(); }
             else cp_async_wait<0>();
             __syncthreads();
             const cplx* T = tiles + buf * E_TILE;
@@ -668,6 +681,7 @@ __device__ __noinline__ void apply_window_transform(cplx* Hb, cplx* Zb, int ld, 
             __syncthreads();
         }
     }
+    hqr_cluster_sync(csize);
 }
 
 __device__ __forceinline__ int block_max_int(int v, int* scratch) {
@@ -682,7 +696,7 @@ __device__ __forceinline__ int block_max_int(int v, int* scratch) {
 }
 
 // status: 0 ok, 1 = QR did not converge
-__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out, long long* prof, int max_trains, int aed_nw, int nibble) {
+__global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, long long stride, int ld, const int* lv, int* status, int* sweeps_out, long long* prof, int max_trains, int aed_nw, int nibble, int csize) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* Hw = reinterpret_cast<cplx*>(smem_raw);
     cplx* Ww = Hw + E_MAT;
@@ -690,7 +704,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
     cplx* Hs = tiles + 2 * E_TILE;            // E_LDS x E_NB
     cplx* shifts = Hs + E_LDS * E_NB;         // E_NB (+ padding to 64)
     int* iscr = reinterpret_cast<int*>(shifts + 64);   // 64 ints
-    const int b = blockIdx.x, n = lv[b];
+    // csize CTAs (one thread-block cluster) per member: all of them run the window computations redundantly and share the strips
+    const int b = blockIdx.x / csize, crank = blockIdx.x % csize, n = lv[b];
     cplx* Hb = H + (long long)b * stride;
     cplx* Zb = Z + (long long)b * stride;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -728,11 +743,13 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             __syncthreads();
             if (iscr[32] < 0) { failed = true; break; }
             PROF(5);
+            // strips first (they never touch the window block), cluster barrier, then the window itself: a CTA of the cluster that is
+            // still loading this window must not see another CTA's post-transform values
+            apply_window_transform(Hb, Zb, ld, n, ilo, ihi + 1, Ww, tiles, iscr + 40, crank, csize);
             for (int idx = tid; idx < size * size; idx += E_THREADS) {
                 int r = idx % size, c = idx / size;
                 Hb[(ilo + r) + (long long)ld * (ilo + c)] = Hw[r + E_LDH * c];
             }
-            apply_window_transform(Hb, Zb, ld, n, ilo, ihi + 1, Ww, tiles, iscr + 40);
             PROF(4);
             ihi = ilo - 1; its = 0;
             continue;
@@ -765,12 +782,12 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             if (ns < 0) { failed = true; break; }
             const int nd = nw - ns;
             if (iscr[33]) {
+                apply_window_transform(Hb, Zb, ld, n, kwtop, ihi + 1, Ww, tiles, iscr + 40, crank, csize);
                 for (int idx = tid; idx < nw * nw; idx += E_THREADS) {
                     int r = idx % nw, c = idx / nw;
                     Hb[(kwtop + r) + (long long)ld * (kwtop + c)] = (r <= c + 1) ? Hw[r + E_LDH * c] : mkc(0.0, 0.0);
                 }
                 if (tid == 0) Hb[kwtop + (long long)ld * (kwtop - 1)] = Hs[64];
-                apply_window_transform(Hb, Zb, ld, n, kwtop, ihi + 1, Ww, tiles, iscr + 40);
             }
             PROF(8);
             if (nd > 0) { ihi -= nd; its = 0; }
@@ -860,18 +877,18 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
                 __syncthreads();
             }
             PROF(2);
+            apply_window_transform(Hb, Zb, ld, n, ws, we, Ww, tiles, iscr + 40, crank, csize);
+            PROF(4);
             for (int idx = tid; idx < ww * ww; idx += E_THREADS) {
                 int r = idx % ww, c = idx / ww;
                 Hb[(ws + r) + (long long)ld * (ws + c)] = Hw[r + E_LDH * c];
             }
             PROF(3);
-            apply_window_transform(Hb, Zb, ld, n, ws, we, Ww, tiles, iscr + 40);
-            PROF(4);
             tstep += T;
         }
         }
     }
-    if (tid == 0) {
+    if (tid == 0 && crank == 0) {
         if (failed) atomicMax(&status[b], 1);
         if (sweeps_out) sweeps_out[b] = nsweeps;
         if (prof) for (int i = 0; i < 10; ++i) prof[10 * b + i] = tp[i];

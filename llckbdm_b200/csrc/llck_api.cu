@@ -764,8 +764,46 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         int aed_nw = E_NW, nibble = 0;      // 0: adaptive
         if (const char* ev = getenv("LLCK_AED_NIBBLE")) { int v = atoi(ev); if (v >= 1 && v <= 1000) nibble = v; }
         if (const char* ev = getenv("LLCK_AED_NW")) { int v = atoi(ev); if (v >= 8 && v <= 48) aed_nw = v; }
-        hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains, aed_nw, nibble);
-        CK(cudaGetLastError());
+        // small batches: a thread-block cluster of csize CTAs per member shares the strip GEMMs (the window chase / AED run redundantly in
+        // every CTA of the cluster); csize = largest power of two that still gives every cluster its own SMs
+        int csize = 1;
+        {
+            int dev = 0, sms = 148;
+            CK(cudaGetDevice(&dev));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            while (csize < 16 && 2 * csize * batch <= sms) csize *= 2;
+            if (const char* ev = getenv("LLCK_HQR_CLUSTER")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) csize = v; }
+        }
+        if (csize == 1) {
+            hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains, aed_nw, nibble, 1);
+            CK(cudaGetLastError());
+        } else {
+            if (csize > 8) CK(cudaFuncSetAttribute(hqr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute attr[1];
+            cfg.blockDim = dim3(E_THREADS); cfg.dynamicSmemBytes = HQR_SMEM_BYTES; cfg.stream = st;
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            for (;;) {                          // fall back to smaller clusters until all of them are co-resident (GPC packing)
+                cfg.gridDim = dim3(batch * csize);
+                attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                int nclusters = 0;
+                cudaError_t eo = cudaOccupancyMaxActiveClusters(&nclusters, hqr_kernel, &cfg);
+                if (verbose) fprintf(stderr, "[llck] hqr: cluster size %d -> max active clusters %d (err %d)\n", csize, nclusters, (int)eo);
+                if (eo == cudaSuccess && nclusters >= batch) break;      // every member's cluster resident in ONE wave
+                (void)cudaGetLastError();
+                csize /= 2;
+                if (csize == 1) break;
+            }
+            if (csize == 1) {
+                hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains, aed_nw, nibble, 1);
+                CK(cudaGetLastError());
+            } else {
+                cplx* aH = bH; cplx* aZ = bZ; long long astride = stride; int ald = ld; const int* alv = d_lv; int* ast = status; int* ahq = d_hqrs;
+                CK(cudaLaunchKernelEx(&cfg, hqr_kernel, aH, aZ, astride, ald, alv, ast, ahq, d_prof, hqr_trains, aed_nw, nibble, csize));
+            }
+        }
+        if (verbose) fprintf(stderr, "[llck] hqr: %d CTA(s) per member\n", csize);
         if (verbose) {
             long long* hp = (long long*)malloc(sizeof(long long) * 10 * batch);
             CK(cudaMemcpyAsync(hp, d_prof, sizeof(long long) * 10 * batch, cudaMemcpyDeviceToHost, st));
