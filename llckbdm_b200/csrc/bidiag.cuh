@@ -16,7 +16,8 @@
 // dynamic smem: (2*ld + 2*BD_NB*BD_NB + 8*BD_NB + 8) * 16 + 512
 __global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, long long stride, int ld, const int* mv, int k0,
                                                                     cplx* Vp, cplx* Yp, cplx* Xp, cplx* Up, long long pstride,
-                                                                    cplx* TQws, cplx* TPws, long long tstride, double* dws, double* ews) {
+                                                                    cplx* TQws, cplx* TPws, long long tstride, double* dws, double* ews,
+                                                                    cplx* ypart, int csize) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* vvec = reinterpret_cast<cplx*>(smem_raw);       // ld : column work vector, then v
     cplx* uvec = vvec + ld;                                // ld : y, then conj(row), then u
@@ -31,13 +32,17 @@ __global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, lon
     cplx* vrow = zu + BD_NB;                               // V[c, :i+1]
     cplx* xrow = vrow + BD_NB;                             // X[c, :i]
     double* red = reinterpret_cast<double*>(xrow + BD_NB + 8);
-    const int b = blockIdx.x, m = mv[b];
+    // csize > 1 (small batches): a thread-block cluster per member.  Every CTA runs the O(m) bookkeeping redundantly (bit-identical);
+    // pass 1 is split by column pairs, pass 2 by column ranges with partial sums through ypart[member][parity][rank][ld]; the writes of
+    // the reflectors into A are deferred behind the cluster barriers so that no CTA sees them while it still needs the old column / row.
+    const int b = blockIdx.x / csize, crank = blockIdx.x % csize, m = mv[b];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     cplx* Ab = A + (long long)b * stride;
     cplx* Vb = Vp + (long long)b * pstride;
     cplx* Yb = Yp + (long long)b * pstride;
     cplx* Xb = Xp + (long long)b * pstride;
     cplx* Ub = Up + (long long)b * pstride;
+    cplx* ypb = (csize > 1) ? ypart + (long long)b * 2 * csize * ld : nullptr;
     if (k0 >= m) {                                         // member already finished: neutral panel for the batched updates
         for (int idx = tid; idx < ld * BD_NB; idx += E_THREADS) {
             Vb[idx] = mkc(0.0, 0.0); Yb[idx] = mkc(0.0, 0.0); Xb[idx] = mkc(0.0, 0.0); Ub[idx] = mkc(0.0, 0.0);
@@ -85,8 +90,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, lon
         __syncthreads();
         for (int r = c + tid; r < m; r += E_THREADS) {
             cplx vv;
-            if (r == c) { vv = mkc(1.0, 0.0); Ab[c + (long long)ld * c] = mkc(beta, 0.0); }
-            else { vv = trivial ? mkc(0.0, 0.0) : cmul(vvec[r], scale); Ab[r + (long long)ld * c] = vv; }
+            if (r == c) { vv = mkc(1.0, 0.0); if (csize == 1) Ab[c + (long long)ld * c] = mkc(beta, 0.0); }
+            else { vv = trivial ? mkc(0.0, 0.0) : cmul(vvec[r], scale); if (csize == 1) Ab[r + (long long)ld * c] = vv; }
             vvec[r] = vv;
             Vb[r + (long long)ld * i] = vv;
         }
@@ -108,9 +113,16 @@ __global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, lon
             TQ[tid + BD_NB * i] = cneg(cmul(tau, a));
         }
         if (tid == 0) TQ[i + BD_NB * i] = tau;
-        if (c + 1 >= m) { __syncthreads(); continue; }
+        if (c + 1 >= m) {
+            if (csize > 1) {                    // last column: store its reflector once every CTA of the cluster has read the old column
+                cluster_barrier(csize);
+                for (int r = c + tid; r < m; r += E_THREADS) Ab[r + (long long)ld * c] = (r == c) ? mkc(beta, 0.0) : vvec[r];
+            }
+            __syncthreads();
+            continue;
+        }
         // ---------- y = tau (A^H v - Y zv - U zx) on columns j > c   (pass 1 over the trailing matrix: column dots) ----------
-        for (int j = c + 1 + 2 * warp; j < m; j += 2 * E_NWARPS) {          // two columns per warp, 4 independent loads each
+        for (int j = c + 1 + 2 * (warp + E_NWARPS * crank); j < m; j += 2 * E_NWARPS * csize) {   // two columns per warp, 4 independent loads each
             const bool two = (j + 1 < m);
             const cplx* col0 = Ab + (long long)ld * j;
             const cplx* col1 = Ab + (long long)ld * (two ? j + 1 : j);
@@ -136,6 +148,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, lon
                 Yb[jc + (long long)ld * i] = cmul(tau, d);
             }
         }
+        cluster_barrier(csize);                 // column i of Y is complete (its entries were computed by different CTAs of the cluster)
         if (tid <= i) vrow[tid] = Vb[c + (long long)ld * tid];
         if (tid < i) xrow[tid] = Xb[c + (long long)ld * tid];
         __syncthreads();
@@ -163,8 +176,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, lon
         __syncthreads();
         for (int j = c + 1 + tid; j < m; j += E_THREADS) {
             cplx uu;
-            if (j == c + 1) { uu = mkc(1.0, 0.0); Ab[c + (long long)ld * j] = mkc(beta2, 0.0); }
-            else { uu = triv2 ? mkc(0.0, 0.0) : cmul(uvec[j], scale2); Ab[c + (long long)ld * j] = uu; }
+            if (j == c + 1) { uu = mkc(1.0, 0.0); if (csize == 1) Ab[c + (long long)ld * j] = mkc(beta2, 0.0); }
+            else { uu = triv2 ? mkc(0.0, 0.0) : cmul(uvec[j], scale2); if (csize == 1) Ab[c + (long long)ld * j] = uu; }
             uvec[j] = uu;
             Ub[j + (long long)ld * i] = uu;
         }
@@ -188,23 +201,42 @@ __global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, lon
         }
         if (tid == 0) TP[i + BD_NB * i] = pi_;
         // ---------- x = pi (A u - V zy - X zu) on rows r > c   (pass 2 over the trailing matrix: row dots) ----------
-        for (int r = c + 1 + tid; r < m; r += E_THREADS) {
-            const cplx* row = Ab + r + (long long)ld * (c + 1);
-            const cplx* uu = uvec + (c + 1);
+        {
             const int len = m - c - 1;
-            cplx y0 = mkc(0.0, 0.0), y1 = mkc(0.0, 0.0), y2 = mkc(0.0, 0.0), y3 = mkc(0.0, 0.0);
-            int q = 0;
-            for (; q + 7 < len; q += 8) {
-                cplx a0 = row[(long long)ld * q], a1 = row[(long long)ld * (q + 1)], a2 = row[(long long)ld * (q + 2)], a3 = row[(long long)ld * (q + 3)];
-                cplx a4 = row[(long long)ld * (q + 4)], a5 = row[(long long)ld * (q + 5)], a6 = row[(long long)ld * (q + 6)], a7 = row[(long long)ld * (q + 7)];
-                y0 = cfma(a0, uu[q], y0); y1 = cfma(a1, uu[q + 1], y1); y2 = cfma(a2, uu[q + 2], y2); y3 = cfma(a3, uu[q + 3], y3);
-                y0 = cfma(a4, uu[q + 4], y0); y1 = cfma(a5, uu[q + 5], y1); y2 = cfma(a6, uu[q + 6], y2); y3 = cfma(a7, uu[q + 7], y3);
+            const int q0 = (int)(((long long)len * crank) / csize), q1 = (int)(((long long)len * (crank + 1)) / csize);
+            cplx* mine = (csize > 1) ? ypb + ((long long)(i & 1) * csize + crank) * ld : nullptr;
+            for (int r = c + 1 + tid; r < m; r += E_THREADS) {
+                const cplx* row = Ab + r + (long long)ld * (c + 1);
+                const cplx* uu = uvec + (c + 1);
+                cplx y0 = mkc(0.0, 0.0), y1 = mkc(0.0, 0.0), y2 = mkc(0.0, 0.0), y3 = mkc(0.0, 0.0);
+                int q = q0;
+                for (; q + 7 < q1; q += 8) {
+                    cplx a0 = row[(long long)ld * q], a1 = row[(long long)ld * (q + 1)], a2 = row[(long long)ld * (q + 2)], a3 = row[(long long)ld * (q + 3)];
+                    cplx a4 = row[(long long)ld * (q + 4)], a5 = row[(long long)ld * (q + 5)], a6 = row[(long long)ld * (q + 6)], a7 = row[(long long)ld * (q + 7)];
+                    y0 = cfma(a0, uu[q], y0); y1 = cfma(a1, uu[q + 1], y1); y2 = cfma(a2, uu[q + 2], y2); y3 = cfma(a3, uu[q + 3], y3);
+                    y0 = cfma(a4, uu[q + 4], y0); y1 = cfma(a5, uu[q + 5], y1); y2 = cfma(a6, uu[q + 6], y2); y3 = cfma(a7, uu[q + 7], y3);
+                }
+                for (; q < q1; ++q) y0 = cfma(row[(long long)ld * q], uu[q], y0);
+                cplx x = cadd(cadd(y0, y1), cadd(y2, y3));
+                if (csize > 1) { mine[r] = x; continue; }
+                for (int jj = 0; jj <= i; ++jj) x = csub(x, cmul(Vb[r + (long long)ld * jj], zy[jj]));
+                for (int jj = 0; jj < i; ++jj) x = csub(x, cmul(Xb[r + (long long)ld * jj], zu[jj]));
+                Xb[r + (long long)ld * i] = cmul(pi_, x);
             }
-            for (; q < len; ++q) y0 = cfma(row[(long long)ld * q], uu[q], y0);
-            cplx x = cadd(cadd(y0, y1), cadd(y2, y3));
-            for (int jj = 0; jj <= i; ++jj) x = csub(x, cmul(Vb[r + (long long)ld * jj], zy[jj]));
-            for (int jj = 0; jj < i; ++jj) x = csub(x, cmul(Xb[r + (long long)ld * jj], zu[jj]));
-            Xb[r + (long long)ld * i] = cmul(pi_, x);
+            if (csize > 1) {
+                cluster_barrier(csize);
+                const cplx* parts = ypb + (long long)(i & 1) * csize * ld;
+                for (int r = c + 1 + tid; r < m; r += E_THREADS) {
+                    cplx x = parts[r];
+                    for (int k = 1; k < csize; ++k) x = cadd(x, parts[(long long)k * ld + r]);
+                    for (int jj = 0; jj <= i; ++jj) x = csub(x, cmul(Vb[r + (long long)ld * jj], zy[jj]));
+                    for (int jj = 0; jj < i; ++jj) x = csub(x, cmul(Xb[r + (long long)ld * jj], zu[jj]));
+                    Xb[r + (long long)ld * i] = cmul(pi_, x);          // every CTA writes the same value
+                }
+                // deferred stores of the two reflectors of this step (the whole cluster is past its reads of column c and row c of A)
+                for (int r = c + tid; r < m; r += E_THREADS) Ab[r + (long long)ld * c] = (r == c) ? mkc(beta, 0.0) : vvec[r];
+                for (int j = c + 1 + tid; j < m; j += E_THREADS) Ab[c + (long long)ld * j] = (j == c + 1) ? mkc(beta2, 0.0) : uvec[j];
+            }
         }
         __syncthreads();
     }

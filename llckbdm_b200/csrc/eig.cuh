@@ -20,6 +20,16 @@
 #define E_LDS 17        // ld of the shift scratch matrix
 #define HQR_SMEM_BYTES ((2 * E_MAT + 2 * E_TILE + E_LDS * E_NB + 64) * 16 + 1024)
 
+// Small batches run the one-CTA-per-member kernels as a thread-block cluster of csize CTAs per member: every CTA executes the cheap
+// O(n) bookkeeping redundantly (bit-identical, so redundant global writes are benign) and the O(n^2) pass is split across the cluster.
+// Barrier with release/acquire ordering of global-memory writes inside the cluster.
+__device__ __forceinline__ void cluster_barrier(int csize) {
+    if (csize > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Hessenberg reduction + Q formation
 // ---------------------------------------------------------------------------------------------
@@ -129,7 +139,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hessenberg_kernel(cplx* H, cplx*
 #define HB_NB 32
 __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long long stride, int ld, const int* lv, int k0,
                                                                   cplx* Vp, cplx* Yp, cplx* VTp, long long pstride,
-                                                                  cplx* Tws, long long tstride) {
+                                                                  cplx* Tws, long long tstride, cplx* ypart, int csize) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* bvec = reinterpret_cast<cplx*>(smem_raw);       // ld
     cplx* vvec = bvec + ld;                                // ld
@@ -139,12 +149,15 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
     cplx* zv = w2 + HB_NB;                                 // HB_NB
     cplx* vrow = zv + HB_NB;                               // HB_NB : conj(V[c, :j])
     double* red = reinterpret_cast<double*>(vrow + HB_NB);
-    const int b = blockIdx.x, n = lv[b];
+    // csize > 1: cluster of CTAs per member -- the gemv over the trailing matrix is split by COLUMNS (every thread keeps its row),
+    // partial sums go through ypart[member][parity][rank][ld] and one cluster barrier per column
+    const int b = blockIdx.x / csize, crank = blockIdx.x % csize, n = lv[b];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     cplx* Hb = H + (long long)b * stride;
     cplx* Vb = Vp + (long long)b * pstride;
     cplx* Yb = Yp + (long long)b * pstride;
     cplx* VTb = VTp + (long long)b * pstride;
+    cplx* ypb = (csize > 1) ? ypart + (long long)b * 2 * csize * ld : nullptr;
     if (k0 + 2 >= n) {                                     // nothing left to reduce for this member: neutral panel
         for (int idx = tid; idx < ld * HB_NB; idx += E_THREADS) { Vb[idx] = mkc(0.0, 0.0); Yb[idx] = mkc(0.0, 0.0); VTb[idx] = mkc(0.0, 0.0); }
         return;
@@ -193,6 +206,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
         }
         if (c + 2 >= n) {
             // last two columns of the matrix: no reflector, just store the updated column
+            cluster_barrier(csize);             // every CTA of the cluster has read the old column before anyone overwrites it
             for (int i = tid; i < n; i += E_THREADS) colc[i] = bvec[i];
             __syncthreads();
             continue;
@@ -218,8 +232,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
             else if (i > c + 1) { vv = trivial ? mkc(0.0, 0.0) : cmul(bvec[i], scale); hv = vv; }
             vvec[i] = vv;
             Vb[i + (long long)ld * j] = vv;
-            colc[i] = hv;                       // Hessenberg column above/at the subdiagonal, v stored below it
-        }
+            if (csize == 1) colc[i] = hv;       // Hessenberg column above/at the subdiagonal, v stored below it
+        }                                       // (cluster: written after the barrier below -- a slower CTA may still be reading the old column)
         __syncthreads();
         // ---- z = V[:, :j]^H v ;  T[:j, j] = -tau T[:j,:j] z ; T[j,j] = tau ----
         for (int jj = warp; jj < j; jj += E_NWARPS) {
@@ -237,22 +251,41 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
         }
         if (tid == 0) Tsm[j + HB_NB * j] = tau;
         // ---- y = tau (A[:, c+1:] v[c+1:] - Y[:, :j] z)  (the one pass over the trailing matrix) ----
-        for (int i = tid; i < n; i += E_THREADS) {
-            const cplx* row = Hb + i + (long long)ld * (c + 1);
-            const cplx* vv = vvec + (c + 1);
+        {
             const int len = n - c - 1;
-            cplx y0 = mkc(0.0, 0.0), y1 = mkc(0.0, 0.0), y2 = mkc(0.0, 0.0), y3 = mkc(0.0, 0.0);
-            int q = 0;
-            for (; q + 7 < len; q += 8) {
-                cplx a0 = row[(long long)ld * q], a1 = row[(long long)ld * (q + 1)], a2 = row[(long long)ld * (q + 2)], a3 = row[(long long)ld * (q + 3)];
-                cplx a4 = row[(long long)ld * (q + 4)], a5 = row[(long long)ld * (q + 5)], a6 = row[(long long)ld * (q + 6)], a7 = row[(long long)ld * (q + 7)];
-                y0 = cfma(a0, vv[q], y0); y1 = cfma(a1, vv[q + 1], y1); y2 = cfma(a2, vv[q + 2], y2); y3 = cfma(a3, vv[q + 3], y3);
-                y0 = cfma(a4, vv[q + 4], y0); y1 = cfma(a5, vv[q + 5], y1); y2 = cfma(a6, vv[q + 6], y2); y3 = cfma(a7, vv[q + 7], y3);
+            const int q0 = (int)(((long long)len * crank) / csize), q1 = (int)(((long long)len * (crank + 1)) / csize);
+            cplx* mine = (csize > 1) ? ypb + ((long long)(j & 1) * csize + crank) * ld : nullptr;
+            for (int i = tid; i < n; i += E_THREADS) {
+                const cplx* row = Hb + i + (long long)ld * (c + 1);
+                const cplx* vv = vvec + (c + 1);
+                cplx y0 = mkc(0.0, 0.0), y1 = mkc(0.0, 0.0), y2 = mkc(0.0, 0.0), y3 = mkc(0.0, 0.0);
+                int q = q0;
+                for (; q + 7 < q1; q += 8) {
+                    cplx a0 = row[(long long)ld * q], a1 = row[(long long)ld * (q + 1)], a2 = row[(long long)ld * (q + 2)], a3 = row[(long long)ld * (q + 3)];
+                    cplx a4 = row[(long long)ld * (q + 4)], a5 = row[(long long)ld * (q + 5)], a6 = row[(long long)ld * (q + 6)], a7 = row[(long long)ld * (q + 7)];
+                    y0 = cfma(a0, vv[q], y0); y1 = cfma(a1, vv[q + 1], y1); y2 = cfma(a2, vv[q + 2], y2); y3 = cfma(a3, vv[q + 3], y3);
+                    y0 = cfma(a4, vv[q + 4], y0); y1 = cfma(a5, vv[q + 5], y1); y2 = cfma(a6, vv[q + 6], y2); y3 = cfma(a7, vv[q + 7], y3);
+                }
+                for (; q < q1; ++q) y0 = cfma(row[(long long)ld * q], vv[q], y0);
+                cplx y = cadd(cadd(y0, y1), cadd(y2, y3));
+                if (csize > 1) { mine[i] = y; continue; }
+                for (int jj = 0; jj < j; ++jj) y = csub(y, cmul(Yb[i + (long long)ld * jj], zv[jj]));
+                Yb[i + (long long)ld * j] = cmul(tau, y);
             }
-            for (; q < len; ++q) y0 = cfma(row[(long long)ld * q], vv[q], y0);
-            cplx y = cadd(cadd(y0, y1), cadd(y2, y3));
-            for (int jj = 0; jj < j; ++jj) y = csub(y, cmul(Yb[i + (long long)ld * jj], zv[jj]));
-            Yb[i + (long long)ld * j] = cmul(tau, y);
+            if (csize > 1) {
+                cluster_barrier(csize);
+                const cplx* parts = ypb + (long long)(j & 1) * csize * ld;
+                for (int i = tid; i < n; i += E_THREADS) {
+                    cplx y = parts[i];
+                    for (int r = 1; r < csize; ++r) y = cadd(y, parts[(long long)r * ld + i]);
+                    for (int jj = 0; jj < j; ++jj) y = csub(y, cmul(Yb[i + (long long)ld * jj], zv[jj]));
+                    Yb[i + (long long)ld * j] = cmul(tau, y);      // every CTA writes the same value
+                    cplx hv = bvec[i];
+                    if (i == c + 1) hv = trivial ? alpha : mkc(beta, 0.0);
+                    else if (i > c + 1) hv = vvec[i];
+                    colc[i] = hv;
+                }
+            }
         }
         __syncthreads();
     }

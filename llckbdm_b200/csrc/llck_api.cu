@@ -72,7 +72,7 @@ __global__ void bdc_fallback_count_kernel(const int* fallback, int* done, int* c
 
 // ---- workspace layout -----------------------------------------------------------------------------
 struct WsLayout {
-    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, bdcvec, fallback, mats, total;
+    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, bdcvec, fallback, ypart, mats, total;
     int nmats;
 };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -106,6 +106,8 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
     L.offws = o; o = al256(o + sizeof(double) * (size_t)batch * pairs_max);
     L.bdcvec = o; o = al256(o + bdc_vec_bytes(batch, 2 * ld));
     L.fallback = o; o = al256(o + sizeof(int) * batch);
+    // partial gemv results of the cluster-cooperative panel kernels (small batches only: [member][parity][rank <= 16][ld])
+    L.ypart = o; o = al256(o + sizeof(cplx) * (size_t)(batch <= 74 ? batch : 0) * 2 * 16 * ld);
     L.mats = o;
     // 6 pipeline matrices (14 in debug mode) + 5 for the divide-and-conquer SVD of the bidiagonal (two 2ld x 2ld real
     // eigenvector buffers and the secular eigenvector matrices)
@@ -116,23 +118,72 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
 }
 
 
+// Portable cluster size only: 16-CTA clusters were measured bimodal across processes (hqr of one m=1024 member 187 ms or ~500 ms
+// depending on where the hardware places the cluster), 8-CTA clusters repeatable (220 ms).
+#define LLCK_MAX_CLUSTER 8
+
+// ---- thread-block cluster launches for small batches ----------------------------------------------------------------
+// largest power-of-two cluster size (<= 16) such that all `batch` clusters of `kernel` are co-resident in one wave
+template <typename K>
+static int pick_cluster_size(K kernel, int batch, int threads, size_t smem, int max_size) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+    int csize = 1;
+    while (csize < max_size && 2 * csize * batch <= sms) csize *= 2;
+    if (const char* ev = getenv("LLCK_CLUSTER")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) csize = v < max_size ? v : max_size; }
+    if (csize > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { (void)cudaGetLastError(); csize = 8; }
+    while (csize > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.gridDim = dim3(batch * csize);
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nclusters = 0;
+        cudaError_t eo = cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg);
+        // all clusters co-resident in ONE wave, with 1/8 head-room: at exactly full occupancy (74 pairs on 148 SMs) a second wave was observed
+        if (eo == cudaSuccess && nclusters >= batch + (batch + 7) / 8) break;
+        (void)cudaGetLastError();
+        csize /= 2;
+    }
+    return csize;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_clustered(void (*kernel)(KArgs...), int batch, int csize, int threads, size_t smem, cudaStream_t st, Args... args) {
+    if (csize <= 1) {
+        kernel<<<batch, threads, smem, st>>>(args...);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.gridDim = dim3(batch * csize); cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+
 // ---- blocked bidiagonalisation driver (shared by llck_kbdm_batched and the stage test entry) ---------------------
 // A (in: matrices, out: reflectors + d/e), Q and P (out, ld x m each), panel buffers Vp/Yp/Xp/Up (ld x 32 each), Wp (32 x ld),
 // TQws/TPws ((ld/32) x 32 x 32 each), dws/ews (ld doubles each) -- all per member with the given strides.
 static int bidiag_driver(cplx* A, cplx* Q, cplx* P, long long stride, int ld, const int* d_mv, int mmax, int batch,
                          cplx* VX, cplx* YU, cplx* Wp, long long pstride, cplx* TQws, cplx* TPws,
-                         double* dws, double* ews, cudaStream_t st) {
+                         double* dws, double* ews, cudaStream_t st, cplx* ypart = nullptr) {
     // VX = per member [V | X] (ld x 64), YU = per member [Y | U] (ld x 64): the panel's trailing update
     //   A[e:, e:] -= V Y^H + X U^H  is ONE rank-64 GEMM  A[e:, e:] -= [V X] [Y U]^H
     const long long pstride2 = 2 * pstride;
     cplx* Vp = VX; cplx* Xp = VX + pstride; cplx* Yp = YU; cplx* Up = YU + pstride;
     size_t sm = (size_t)(2 * ld + 2 * BD_NB * BD_NB + 8 * BD_NB + 8) * 16 + 512;
     CK(cudaFuncSetAttribute(bidiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int bp_csize = (ypart != nullptr && batch <= 74) ? pick_cluster_size(bidiag_panel_kernel, batch, E_THREADS, sm, LLCK_MAX_CLUSTER) : 1;
     int k0_last = 0;
     for (int k0 = 0; k0 < mmax; k0 += BD_NB) {
         k0_last = k0;
-        bidiag_panel_kernel<<<batch, E_THREADS, sm, st>>>(A, stride, ld, d_mv, k0, Vp, Yp, Xp, Up, pstride2, TQws, TPws, pstride, dws, ews);
-        CK(cudaGetLastError());
+        CK(launch_clustered(bidiag_panel_kernel, batch, bp_csize, E_THREADS, sm, st, A, stride, ld, d_mv, k0, Vp, Yp, Xp, Up, pstride2, TQws, TPws, pstride,
+                            dws, ews, ypart, bp_csize));
         const int e = k0 + BD_NB;
         if (e >= mmax) continue;
         GemmParams g = gemm_params_zero();
@@ -395,7 +446,8 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         {
             // [V|X] lives in the (vp, yp) pair of panel buffers, [Y|U] in (vtp, wp): both pairs are contiguous in the workspace
             int rc = bidiag_driver(bX, bQ, bPm, stride, ld, d_mv, mmax, batch, (cplx*)(ws + L.vp), (cplx*)(ws + L.vtp),
-                                   (cplx*)(ws + L.pan6), pstride, (cplx*)(ws + L.tws), (cplx*)(ws + L.pan7), dws, ews, st);
+                                   (cplx*)(ws + L.pan6), pstride, (cplx*)(ws + L.tws), (cplx*)(ws + L.pan7), dws, ews, st,
+                                   (cplx*)(ws + L.ypart));
             if (rc) return rc;
         }
         TICK();   // 1: init + bidiagonalisation done
@@ -689,12 +741,14 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             const long long pstride = (long long)ld * HB_NB;
             size_t sm = (size_t)(2 * ld + HB_NB * HB_NB + 4 * HB_NB) * 16 + 512;
             CK(cudaFuncSetAttribute(hess_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            const int hp_csize = (batch <= 74) ? pick_cluster_size(hess_panel_kernel, batch, E_THREADS, sm, LLCK_MAX_CLUSTER) : 1;
+            if (verbose) fprintf(stderr, "[llck] hess_panel: %d CTA(s) per member\n", hp_csize);
             GemmParams hp = gemm_params_zero();
             int k0_last = 0;
             for (int k0 = 0; k0 + 2 < lmax; k0 += HB_NB) {
                 k0_last = k0;
-                hess_panel_kernel<<<batch, E_THREADS, sm, st>>>(bH, stride, ld, d_lv, k0, Vp, Yp, VTp, pstride, Tws, pstride);
-                CK(cudaGetLastError());
+                CK(launch_clustered(hess_panel_kernel, batch, hp_csize, E_THREADS, sm, st, bH, stride, ld, d_lv, k0, Vp, Yp, VTp, pstride, Tws, pstride,
+                                    (cplx*)(ws + L.ypart), hp_csize));
                 const int e = k0 + HB_NB;
                 if (e >= lmax) continue;
                 // A[:, e:] -= Y * V[e:, :]^H
@@ -766,43 +820,8 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         if (const char* ev = getenv("LLCK_AED_NW")) { int v = atoi(ev); if (v >= 8 && v <= 48) aed_nw = v; }
         // small batches: a thread-block cluster of csize CTAs per member shares the strip GEMMs (the window chase / AED run redundantly in
         // every CTA of the cluster); csize = largest power of two that still gives every cluster its own SMs
-        int csize = 1;
-        {
-            int dev = 0, sms = 148;
-            CK(cudaGetDevice(&dev));
-            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            while (csize < 16 && 2 * csize * batch <= sms) csize *= 2;
-            if (const char* ev = getenv("LLCK_HQR_CLUSTER")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) csize = v; }
-        }
-        if (csize == 1) {
-            hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains, aed_nw, nibble, 1);
-            CK(cudaGetLastError());
-        } else {
-            if (csize > 8) CK(cudaFuncSetAttribute(hqr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            cudaLaunchConfig_t cfg = {};
-            cudaLaunchAttribute attr[1];
-            cfg.blockDim = dim3(E_THREADS); cfg.dynamicSmemBytes = HQR_SMEM_BYTES; cfg.stream = st;
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            for (;;) {                          // fall back to smaller clusters until all of them are co-resident (GPC packing)
-                cfg.gridDim = dim3(batch * csize);
-                attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                int nclusters = 0;
-                cudaError_t eo = cudaOccupancyMaxActiveClusters(&nclusters, hqr_kernel, &cfg);
-                if (verbose) fprintf(stderr, "[llck] hqr: cluster size %d -> max active clusters %d (err %d)\n", csize, nclusters, (int)eo);
-                if (eo == cudaSuccess && nclusters >= batch) break;      // every member's cluster resident in ONE wave
-                (void)cudaGetLastError();
-                csize /= 2;
-                if (csize == 1) break;
-            }
-            if (csize == 1) {
-                hqr_kernel<<<batch, E_THREADS, HQR_SMEM_BYTES, st>>>(bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains, aed_nw, nibble, 1);
-                CK(cudaGetLastError());
-            } else {
-                cplx* aH = bH; cplx* aZ = bZ; long long astride = stride; int ald = ld; const int* alv = d_lv; int* ast = status; int* ahq = d_hqrs;
-                CK(cudaLaunchKernelEx(&cfg, hqr_kernel, aH, aZ, astride, ald, alv, ast, ahq, d_prof, hqr_trains, aed_nw, nibble, csize));
-            }
-        }
+        const int csize = (batch <= 74) ? pick_cluster_size(hqr_kernel, batch, E_THREADS, HQR_SMEM_BYTES, LLCK_MAX_CLUSTER) : 1;
+        CK(launch_clustered(hqr_kernel, batch, csize, E_THREADS, HQR_SMEM_BYTES, st, bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains, aed_nw, nibble, csize));
         if (verbose) fprintf(stderr, "[llck] hqr: %d CTA(s) per member\n", csize);
         if (verbose) {
             long long* hp = (long long*)malloc(sizeof(long long) * 10 * batch);
