@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--m", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--c2-full", action="store_true", help="also time llc_kbdm end to end on config C2 (HDBSCAN fits on the host cores: ~1 min)")
     return ap.parse_args()
 
 
@@ -292,6 +293,28 @@ def run_native(args):
         torch.cuda.synchronize()
         out["llc_ensemble_c2"] = {"members": 100, "m_range": "700..1024", "solve_phase_s": time.perf_counter() - t0,
                                   "bad_status_members": int((r2.status != 0).sum()), "note": "host FID in, host line lists out; HDBSCAN clustering not included"}
+    if rank == 0 and world == 1 and not args.no_c2:
+        # single KBDM solve (config C1): one m = l = 1024 member through the public API, host to host (thread-block clusters per member)
+        from llckbdm_b200.kbdm import kbdm
+        c1 = brain_sim(2 * m, SIGMA, 0)
+        kbdm(c1, DWELL, m=m)
+        ts = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            kbdm(c1, DWELL, m=m)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        out["single_solve_c1"] = {"m": m, "seconds": float(np.median(ts)), "note": "kbdm(data, dwell, m) host to host, median of 3"}
+    if rank == 0 and world == 1 and args.c2_full:
+        from llckbdm_b200.llckbdm import llc_kbdm
+        c = brain_sim(2048, SIGMA, 0)
+        m2 = [700 + round(k * 324 / 99) for k in range(100)]
+        t0 = time.perf_counter()
+        r3 = llc_kbdm(c, DWELL, m2)
+        out["llc_ensemble_c2"]["total_with_clustering_s"] = time.perf_counter() - t0
+        out["llc_ensemble_c2"]["clusters"] = int(len(r3.line_list))
+        out["llc_ensemble_c2"]["host_cores"] = os.cpu_count()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import scipy.linalg  # noqa: F401
         use_all_host_threads()

@@ -450,11 +450,13 @@ __device__ __noinline__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, 
 // Returns ns (>= 0), or -1 if the window QR failed.  out[0] = 1 if T/V must be written back.  newsub = new H[kwtop,kwtop-1].
 // ---------------------------------------------------------------------------------------------
 #define E_NW 24        // AED window (measured at m=1024: 16 -> 1280, 24 -> 1135, 32 -> 1188, 40 -> 1397 Mcycles per member)
-__device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shifts, cplx* vbuf, int* out, cplx* newsub) {
+__device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shifts, cplx* vbuf, int* out, cplx* newsub, long long* ap) {
     const int lane = threadIdx.x & 31;
     const int L = E_LDH, LV = E_LDW;       // T lives in Hw (ld E_LDH), V in Ww (ld E_LDW)
+    long long t0 = ap ? clock64() : 0;
     if (warp_small_hqr(T, L, V, LV, nw, nw) < 0) return -1;
     __syncwarp();
+    if (ap) { long long t1 = clock64(); ap[0] += t1 - t0; t0 = t1; }
     int ns = nw, ilst = 0;
     const double s1 = cabs1(s);
     const double smallnum = LLCK_SAFMIN / LLCK_EPS;
@@ -494,6 +496,7 @@ __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shi
             ++ilst;
         }
     }
+    if (ap) { long long t1 = clock64(); ap[1] += t1 - t0; t0 = t1; }
     if (ns == 0) s = mkc(0.0, 0.0);
     for (int j = lane; j < ns; j += 32) shifts[j] = T[j + L * j];
     const bool sz = (s.x == 0.0 && s.y == 0.0);
@@ -581,6 +584,7 @@ __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shi
     }
     if (lane == 0) *newsub = cmul(s, cconj(V[0]));
     __syncwarp();
+    if (ap) ap[2] += clock64() - t0;
     return ns;
 }
 
@@ -746,6 +750,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
     int ihi = n - 1, its = 0, nsweeps = 0;
     bool failed = false;
     long long tp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // scan+shifts, window load, chase, store, strips, small blocks, AED load, AED warp work, AED strips, AED calls
+    __shared__ long long aedprof[3];
+    if (threadIdx.x < 3) aedprof[threadIdx.x] = 0;
     long long tc = clock64();
 #define PROF(i) do { if (prof) { long long tn_ = clock64(); tp[i] += tn_ - tc; tc = tn_; } } while (0)
     while (ihi >= 0) {
@@ -805,7 +811,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             __syncthreads();
             PROF(6);
             if (warp == 0) {
-                int r = warp_aed(Hw, Ww, nw, spike, shifts, Hs, iscr + 33, Hs + 64);
+                int r = warp_aed(Hw, Ww, nw, spike, shifts, Hs, iscr + 33, Hs + 64, prof ? aedprof : nullptr);
                 if (lane == 0) iscr[32] = r;
             }
             __syncthreads();
@@ -924,7 +930,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
     if (tid == 0 && crank == 0) {
         if (failed) atomicMax(&status[b], 1);
         if (sweeps_out) sweeps_out[b] = nsweeps;
-        if (prof) for (int i = 0; i < 10; ++i) prof[10 * b + i] = tp[i];
+        if (prof) { for (int i = 0; i < 10; ++i) prof[10 * b + i] = tp[i]; if (lane == 0) { prof[10 * b + 0] = aedprof[0]; prof[10 * b + 6] = aedprof[1]; } }
     }
 #undef PROF
 }

@@ -829,7 +829,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             CK(cudaStreamSynchronize(st));
             double tot[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (int b = 0; b < batch; ++b) for (int i = 0; i < 10; ++i) tot[i] += (double)hp[10 * b + i] / batch;
-            fprintf(stderr, "[llck] hqr phase Mcycles/member: scan+shifts=%.1f load=%.1f chase=%.1f store=%.1f strips=%.1f small=%.1f | AED: load=%.1f warp=%.1f strips=%.1f calls=%.0f\n",
+            fprintf(stderr, "[llck] hqr phase Mcycles/member: aed_schur=%.1f load=%.1f chase=%.1f store=%.1f strips=%.1f small=%.1f | AED: reorder=%.1f warp_total=%.1f strips=%.1f calls=%.0f\n",
                     tot[0] / 1e6, tot[1] / 1e6, tot[2] / 1e6, tot[3] / 1e6, tot[4] / 1e6, tot[5] / 1e6, tot[6] / 1e6, tot[7] / 1e6, tot[8] / 1e6, tot[9]);
             double mn = 1e300, mx = 0;
             for (int b = 0; b < batch; ++b) {
