@@ -116,6 +116,17 @@ int llck_rmse_batched(const void* data, int32_t N, double dwell, const double* l
 int llck_silhouette_batched(const double* X, int32_t n, const int32_t* order, const int32_t* seg, const int32_t* nseg,
                             const int32_t* cluster_of, int32_t nclusterings, double* out, void* stream);
 
+/* Pooled filtered line lists + clustering features of a solved ensemble -- replaces the host sequence of llckbdm/llckbdm.py:94-98
+ * (np.concatenate of the members' line lists, filter_samples of llckbdm/sampling.py:75-97, _transform_line_lists of
+ * llckbdm/llckbdm.py:202-230) by one launch that reads the solver's output buffer.  Rows keep member order and row order.
+ *   line_lists  device float64 [batch][ll_stride] as written by llck_kbdm_batched;  n_rows device int32 [batch] (= l)
+ *   offset      device int64 [batch]: first output row of each member = exclusive prefix sum of the members' valid-row counts
+ *               (the n_valid output of llck_kbdm_batched)
+ *   samples     device float64 [total][4]: kept rows (A, T2, F, PH);   features  device float64 [total][4]: (Re mu, Im mu, A, 0),
+ *               mu = exp(i dwell (2 pi F + i/T2)).  Stream-ordered, asynchronous.                                              */
+int llck_pool_features(const double* line_lists, int64_t ll_stride, const int32_t* n_rows, const int64_t* offset, int32_t batch,
+                       double dwell, double amplitude_tol, double* samples, double* features, void* stream);
+
 /* Stage entry (tests): divide-and-conquer SVD of `batch` real upper-bidiagonal matrices (second half of the replacement of
  * scipy.linalg.svd, llckbdm/kbdm.py:166).  d, e: device [batch][ld] (diagonal m, super-diagonal m-1); m: host [batch];
  * ld multiple of 64.  Outputs (device): sing_vals [batch][ld] descending, Us = U*diag(s) and V as complex128 [batch][ld*ld]

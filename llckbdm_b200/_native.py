@@ -21,6 +21,7 @@ SYMBOLS = (
     "llck_bdc_test",
     "llck_rmse_batched",
     "llck_silhouette_batched",
+    "llck_pool_features",
 )
 
 FLAG_DEBUG_KEEP = 1
@@ -79,6 +80,8 @@ def load():
     lib.llck_rmse_batched.argtypes = [c_vp, c_int, c_dbl, c_vp, c_i64, c_vp, c_int, c_int, c_dbl, c_vp, c_vp]
     lib.llck_silhouette_batched.restype = c_int
     lib.llck_silhouette_batched.argtypes = [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]
+    lib.llck_pool_features.restype = c_int
+    lib.llck_pool_features.argtypes = [c_vp, c_i64, c_vp, c_vp, c_int, c_dbl, c_dbl, c_vp, c_vp, c_vp]
     _lib = lib
     return lib
 

@@ -17,6 +17,7 @@
 #include "bdc.cuh"
 #include "rmse.cuh"
 #include "silhouette.cuh"
+#include "features.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -304,6 +305,15 @@ int llck_silhouette_batched(const double* X, int32_t n, const int32_t* order, co
     if (!X || !order || !seg || !nseg || !cluster_of || !out || n < 1 || nclusterings < 1 || nclusterings > 65535) return LLCK_E_BADARG;
     dim3 grid((n + SIL_THREADS - 1) / SIL_THREADS, nclusterings);
     silhouette_kernel<<<grid, SIL_THREADS, 0, (cudaStream_t)stream>>>(X, n, order, seg, nseg, cluster_of, out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int llck_pool_features(const double* line_lists, int64_t ll_stride, const int32_t* n_rows, const int64_t* offset, int32_t batch,
+                       double dwell, double amplitude_tol, double* samples, double* features, void* stream) {
+    if (!line_lists || !n_rows || !offset || !samples || !features || batch < 1 || ll_stride < 4 || !(dwell > 0.0)) return LLCK_E_BADARG;
+    pool_features_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(line_lists, ll_stride, n_rows, (const long long*)offset, dwell, amplitude_tol,
+                                                                   samples, features);
     CK(cudaGetLastError());
     return 0;
 }

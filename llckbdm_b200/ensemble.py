@@ -147,6 +147,53 @@ def score_candidates(data, dwell, candidates, filter_rows=False, device=None):
         return [float(x) for x in out.cpu().numpy()]
 
 
+def solve_pooled(signal, m, l, p, q, dwell, device=None, chunk=None, amplitude_tol=1e-6):
+    """Solve an ensemble on ONE shared FID and return the pooled, filtered line lists and their clustering features, both
+    produced on the device from the solver's output buffer (llck_pool_features; replaces the host concatenate / filter_samples /
+    _transform_line_lists of reference llckbdm.py:94-98).
+
+    Returns (samples float64 [n, 4], features float64 [n, 4], status int32 [M]); rows are in member order (the order of ``m``),
+    then in the solver's row order -- the order np.concatenate(sample_kbdm(...)[0]) gives."""
+    torch = _require_cuda()
+    lib = _native.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    M = len(m)
+    m = np.asarray(m, dtype=np.int32)
+    l = np.asarray(l, dtype=np.int32)
+    ld = lib.llck_leading_dim(int(m.max()))
+    flat = np.ascontiguousarray(signal, dtype=np.complex128)
+    status = np.zeros(M, dtype=np.int32)
+    per_member = [None] * M
+    with torch.cuda.device(dev):
+        if chunk is None:
+            chunk = min(M, max_chunk(ld, dev))
+        sig_dev = torch.from_numpy(flat.view(np.float64)).to(dev).view(torch.complex128)
+        order = np.arange(M) if chunk >= M else np.argsort(-(m.astype(np.int64) * 4096 + l), kind="stable")
+        ws = None
+        for c0 in range(0, M, chunk):
+            idx = order[c0:c0 + chunk]
+            r = solve_device(sig_dev, np.zeros(len(idx), dtype=np.int64), m[idx], l[idx], p, q, dwell, workspace=ws, want_mu=False)
+            ws = r["workspace"]
+            counts = r["n_valid"].to(torch.int64)
+            offs = torch.cumsum(counts, 0) - counts
+            total = int(counts.sum().item())
+            status[idx] = r["status"].cpu().numpy()
+            samples = torch.empty((max(total, 1), 4), dtype=torch.float64, device=dev)
+            feats = torch.empty((max(total, 1), 4), dtype=torch.float64, device=dev)
+            rows = torch.from_numpy(np.ascontiguousarray(l[idx], dtype=np.int32)).to(dev)
+            rc = lib.llck_pool_features(r["line_lists"].data_ptr(), int(r["line_lists"].shape[1]) * 4, rows.data_ptr(), offs.data_ptr(),
+                                        len(idx), float(dwell), float(amplitude_tol), samples.data_ptr(), feats.data_ptr(),
+                                        torch.cuda.current_stream(dev).cuda_stream)
+            _native.check_rc(rc, "llck_pool_features")
+            s_h, f_h = samples[:total].cpu().numpy(), feats[:total].cpu().numpy()
+            cuts = np.cumsum(counts.cpu().numpy())[:-1]
+            for k, (sp, fp) in zip(idx, zip(np.split(s_h, cuts), np.split(f_h, cuts))):
+                per_member[k] = (sp, fp)
+    if M == 0:
+        return np.zeros((0, 4)), np.zeros((0, 4)), status
+    return (np.concatenate([pm[0] for pm in per_member]), np.concatenate([pm[1] for pm in per_member]), status)
+
+
 def silhouette_samples_device(features, labelings, device=None):
     """Silhouette coefficient of every point for each labeling of the same points, on the device (llck_silhouette_batched;
     replaces sklearn.metrics.silhouette_samples as called at reference llckbdm.py:291).

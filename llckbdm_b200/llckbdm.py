@@ -18,7 +18,7 @@ import numpy as np
 
 from .metrics import calculate_freq_domain_rmse
 from .min_rmse_kbdm import min_rmse_kbdm
-from .sampling import filter_samples, sample_kbdm
+from .sampling import filter_samples, sample_kbdm, sample_kbdm_pooled  # noqa: F401
 from .ensemble import silhouette_samples_device
 from .sig_gen import gen_t_freq_arrays, multi_fid
 
@@ -62,11 +62,10 @@ def llc_kbdm(data, dwell, m_range, p=1, l=None, q=0.0):
     clustering whose averaged line list has the smallest frequency-domain RMSE."""
     if len(m_range) < 2:
         raise ValueError("size of 'm_range' must be greater than 2.")
-    line_lists, _infos = sample_kbdm(data=data, dwell=dwell, m_range=m_range, p=p, l=l, q=q)
-    if len(line_lists) == 0:
+    # sampling + pooling + filter + feature transform (reference llckbdm.py:76-98) in one device pass
+    samples, features = sample_kbdm_pooled(data=data, dwell=dwell, m_range=m_range, p=p, l=l, q=q)
+    if len(samples) == 0:
         return LlcKbdmResult()
-    samples = filter_samples(np.concatenate(line_lists))
-    features = _transform_line_lists(samples, dwell)
     n_members = len(m_range)
     # HDBSCAN for min_samples = 1..M-1 (reference llckbdm.py:104-116): the fits are independent -> spread over the host cores;
     # the silhouettes of all clusterings are then ONE batched device launch instead of M-1 O(n^2) sklearn calls.

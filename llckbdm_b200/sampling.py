@@ -5,7 +5,7 @@ import logging
 
 import numpy as np
 
-from .ensemble import solve_ensemble
+from .ensemble import solve_ensemble, solve_pooled
 from .kbdm import KbdmInfo, raise_for_status, resolve_m_l
 
 logger = logging.getLogger(__name__)
@@ -56,3 +56,22 @@ def sample_kbdm_scored(data, dwell, m_range, p, l, q=0, filter_invalid_features=
             if res.rmse is not None:
                 rmses.append(float(res.rmse[k]))
     return line_lists, infos, rmses
+
+
+def sample_kbdm_pooled(data, dwell, m_range, p, l, q=0):
+    """What reference llckbdm.py:76-98 builds on the host -- ``sample_kbdm`` over m_range, np.concatenate, ``filter_samples`` and
+    ``_transform_line_lists`` -- in one device pass: returns (samples [n, 4], features [n, 4])."""
+    ms, ls = [], []
+    for m in m_range:
+        logger.info(f'Computing KBDM with m = {m}')
+        mm, ll_ = resolve_m_l(data.size, m, l, p)
+        ms.append(mm)
+        ls.append(ll_)
+    if not ms:
+        return np.zeros((0, 4)), np.zeros((0, 4))
+    if q > 0:
+        logger.debug('Using Tikhonov Regularization with q=%f', q)
+    samples, features, status = solve_pooled(np.asarray(data).ravel(), ms, ls, p, q, dwell)
+    for k, mm in enumerate(ms):
+        raise_for_status(int(status[k]), mm)
+    return samples, features

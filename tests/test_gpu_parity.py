@@ -225,6 +225,23 @@ def test_llc_kbdm_matches_host_clustering_stage(cuda):
     assert np.abs(res.silhouette - sils[k]).max() < 1e-6
 
 
+def test_pooled_samples_and_features_match_host_sequence(cuda):
+    """llck_pool_features (device concatenate + filter_samples + _transform_line_lists) == the host sequence of reference
+    llckbdm.py:94-98 on the same solve: kept rows bit-identical and in the same order, features to 1e-14."""
+    from llckbdm_b200 import llckbdm as L
+    from llckbdm_b200.sampling import filter_samples, sample_kbdm, sample_kbdm_pooled
+    from oracle.kbdm_oracle import brain_sim
+    c = brain_sim(1024, 1e-3, 9)
+    m_range = [40, 300, 64, 129, 17]                      # ragged, unsorted: pooled order must follow m_range
+    samples, feats = sample_kbdm_pooled(c, DWELL, m_range, p=1, l=None)
+    lls, _ = sample_kbdm(c, DWELL, m_range, p=1, l=None)
+    want = filter_samples(np.concatenate(lls))
+    assert samples.shape == want.shape and np.array_equal(samples, want)
+    wf = L._transform_line_lists(want, DWELL)
+    assert np.abs(feats - wf).max() < 1e-14
+    assert np.all(feats[:, 3] == 0.0)
+
+
 def test_singular_member_raises_linalgerror(cuda):
     """Exact zero singular value among the kept ones -> LinAlgError (np.linalg.inv behaviour at kbdm.py:186)."""
     from llckbdm_b200.kbdm import kbdm
