@@ -127,6 +127,18 @@ int llck_silhouette_batched(const double* X, int32_t n, const int32_t* order, co
 int llck_pool_features(const double* line_lists, int64_t ll_stride, const int32_t* n_rows, const int64_t* offset, int32_t batch,
                        double dwell, double amplitude_tol, double* samples, double* features, void* stream);
 
+/* The two O(n^2) stages of the HDBSCAN fits of llckbdm/llckbdm.py:104-116 (one fit per min_samples value on the SAME points),
+ * bit-compatible with sklearn.cluster.HDBSCAN's Euclidean Prim path (the stand-in for the un-vendored `hdbscan` package):
+ * llck_hdbscan_core_distances: core[k-1][i] = distance of point i to its k-th nearest neighbour (itself included), k = 1..kmax
+ *                              (replaces one KD-tree kneighbors query per fit);  X device float64 [n][4], core device [kmax][n].
+ * llck_hdbscan_mst:            Prim's spanning tree of the mutual-reachability graph max(core[a], core[b], |a - b|) for `nfits`
+ *                              fits at once (replaces mst_from_data_matrix per fit); core_row[f] selects the row of `core`
+ *                              (= min_samples - 1); edges in insertion order into mst_src / mst_dst / mst_w [nfits][n-1];
+ *                              min_reach [nfits][n] and cur_src [nfits][n] are scratch.  n <= 131072.  Stream-ordered, asynchronous.  */
+int llck_hdbscan_core_distances(const double* X, int32_t n, int32_t kmax, double* core, void* stream);
+int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32_t* core_row, int32_t nfits,
+                     double* min_reach, int32_t* cur_src, int64_t* mst_src, int64_t* mst_dst, double* mst_w, void* stream);
+
 /* Stage entry (tests): divide-and-conquer SVD of `batch` real upper-bidiagonal matrices (second half of the replacement of
  * scipy.linalg.svd, llckbdm/kbdm.py:166).  d, e: device [batch][ld] (diagonal m, super-diagonal m-1); m: host [batch];
  * ld multiple of 64.  Outputs (device): sing_vals [batch][ld] descending, Us = U*diag(s) and V as complex128 [batch][ld*ld]

@@ -22,6 +22,8 @@ SYMBOLS = (
     "llck_rmse_batched",
     "llck_silhouette_batched",
     "llck_pool_features",
+    "llck_hdbscan_core_distances",
+    "llck_hdbscan_mst",
 )
 
 FLAG_DEBUG_KEEP = 1
@@ -82,6 +84,10 @@ def load():
     lib.llck_silhouette_batched.argtypes = [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]
     lib.llck_pool_features.restype = c_int
     lib.llck_pool_features.argtypes = [c_vp, c_i64, c_vp, c_vp, c_int, c_dbl, c_dbl, c_vp, c_vp, c_vp]
+    lib.llck_hdbscan_core_distances.restype = c_int
+    lib.llck_hdbscan_core_distances.argtypes = [c_vp, c_int, c_int, c_vp, c_vp]
+    lib.llck_hdbscan_mst.restype = c_int
+    lib.llck_hdbscan_mst.argtypes = [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     _lib = lib
     return lib
 

@@ -1,0 +1,119 @@
+// The two O(n^2) stages of the HDBSCAN fits of the LLC-KBDM clustering loop (reference llckbdm/llckbdm.py:104-116 runs one
+// fit per min_samples value 1..M-1 on the SAME points), bit-compatible with the host clusterer that stands in for the
+// un-vendored `hdbscan` package here (sklearn.cluster.HDBSCAN, euclidean metric, Prim path):
+//   core distances : distance to the k-th nearest neighbour, k = 1..K in ONE brute-force pass (sklearn: one KD-tree query per fit)
+//   spanning tree  : Prim's algorithm on the mutual-reachability graph exactly as sklearn's mst_from_data_matrix runs it (start at
+//                    node 0, strict-less updates, lowest index wins ties), one CTA per min_samples value, all fits concurrently
+// Distances are sqrt(((dx^2 + dy^2) + dz^2) + dw^2) with separately rounded multiplies and adds (the host code is compiled
+// without FMA), so the edge lists are identical to the host's and the host's tree condensation yields identical labels.
+#pragma once
+#include "common.cuh"
+
+#define HDB_KMAX 128
+#define HDB_TILE 256
+
+__device__ __forceinline__ double hdb_rdist(const double4 a, const double4 b) {
+    const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+    double d = __dmul_rn(dx, dx);
+    d = __dadd_rn(d, __dmul_rn(dy, dy));
+    d = __dadd_rn(d, __dmul_rn(dz, dz));
+    d = __dadd_rn(d, __dmul_rn(dw, dw));
+    return d;
+}
+
+// core[k-1][i] = distance from point i to its k-th nearest neighbour (itself included), k = 1..K
+__global__ void __launch_bounds__(128) hdb_core_kernel(const double* __restrict__ X, int n, int K, double* __restrict__ core) {
+    __shared__ double4 tile[HDB_TILE];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    const double4 xi = live ? reinterpret_cast<const double4*>(X)[i] : make_double4(0, 0, 0, 0);
+    double best[HDB_KMAX];                       // ascending squared distances (local memory)
+    for (int k = 0; k < K; ++k) best[k] = INFINITY;
+    double worst = INFINITY;
+    for (int t0 = 0; t0 < n; t0 += HDB_TILE) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < HDB_TILE; q += blockDim.x)
+            if (t0 + q < n) tile[q] = reinterpret_cast<const double4*>(X)[t0 + q];
+        __syncthreads();
+        const int cnt = min(HDB_TILE, n - t0);
+        if (live) {
+            for (int q = 0; q < cnt; ++q) {
+                const double d = hdb_rdist(xi, tile[q]);
+                if (d < worst) {
+                    int k = K - 1;
+                    while (k > 0 && best[k - 1] > d) { best[k] = best[k - 1]; --k; }
+                    best[k] = d;
+                    worst = best[K - 1];
+                }
+            }
+        }
+    }
+    if (live) for (int k = 0; k < K; ++k) core[(long long)k * n + i] = __dsqrt_rn(best[k]);
+}
+
+// One CTA per fit f: Prim on max(core_f[a], core_f[b], dist(a, b)).  Edge i of the tree = (src[i], dst[i], w[i]) in insertion order.
+// min_reach / cur_src: per-fit scratch [nfits][n].
+#define HDB_PRIM_THREADS 1024
+__global__ void __launch_bounds__(HDB_PRIM_THREADS) hdb_prim_kernel(const double* __restrict__ X, int n, const double* __restrict__ core,
+                                                                    const int* __restrict__ core_row, double* __restrict__ min_reach,
+                                                                    int* __restrict__ cur_src, long long* __restrict__ mst_src,
+                                                                    long long* __restrict__ mst_dst, double* __restrict__ mst_w) {
+    __shared__ double rv[32];
+    __shared__ int rj[32], rs[32];
+    __shared__ int s_cur;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* cr = core + (long long)core_row[f] * n;
+    double* mr = min_reach + (long long)f * n;
+    int* cs = cur_src + (long long)f * n;
+    for (int j = tid; j < n; j += HDB_PRIM_THREADS) { mr[j] = INFINITY; cs[j] = 1; }      // np.full(inf), np.ones
+    // visited flags of this thread's own points j = tid + 1024 * q live in registers (n <= 1024 * 128)
+    unsigned long long vis0 = 0ull, vis1 = 0ull;
+    int cur = 0;
+    __syncthreads();
+    for (int i = 0; i < n - 1; ++i) {
+        if ((cur & (HDB_PRIM_THREADS - 1)) == tid) {
+            const int q = cur >> 10;
+            if (q < 64) vis0 |= 1ull << q; else vis1 |= 1ull << (q - 64);
+        }
+        const double4 xc = reinterpret_cast<const double4*>(X)[cur];
+        const double cd = cr[cur];
+        double bv = 1.7976931348623157e308;      // DBL_MAX: candidates must be strictly below it
+        int bj = 0, bs = 0;
+        for (int j = tid, q = 0; j < n; j += HDB_PRIM_THREADS, ++q) {
+            const bool visited = (q < 64) ? ((vis0 >> q) & 1ull) : ((vis1 >> (q - 64)) & 1ull);
+            if (visited) continue;
+            double m = mr[j];
+            int src = cs[j];
+            const double pd = __dsqrt_rn(hdb_rdist(xc, reinterpret_cast<const double4*>(X)[j]));
+            const double mrd = fmax(fmax(cd, cr[j]), pd);
+            if (mrd < m) { m = mrd; src = cur; mr[j] = m; cs[j] = cur; }
+            if (m < bv) { bv = m; bj = j; bs = src; }            // ascending j within a thread: strict < keeps the lowest index
+        }
+        // lexicographic (value, index) minimum over the CTA == the sequential scan's "first strictly smaller" rule
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o), os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (ov < bv || (ov == bv && ov < 1.7976931348623157e308 && oj < bj)) { bv = ov; bj = oj; bs = os; }
+        }
+        if (lane == 0) { rv[warp] = bv; rj[warp] = bj; rs[warp] = bs; }
+        __syncthreads();
+        if (warp == 0) {
+            bv = rv[lane]; bj = rj[lane]; bs = rs[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o), os = __shfl_xor_sync(0xffffffffu, bs, o);
+                if (ov < bv || (ov == bv && ov < 1.7976931348623157e308 && oj < bj)) { bv = ov; bj = oj; bs = os; }
+            }
+            if (lane == 0) {
+                mst_src[(long long)f * (n - 1) + i] = bs;
+                mst_dst[(long long)f * (n - 1) + i] = bj;
+                mst_w[(long long)f * (n - 1) + i] = bv;
+                s_cur = bj;
+            }
+        }
+        __syncthreads();
+        cur = s_cur;
+    }
+}

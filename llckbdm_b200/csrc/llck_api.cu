@@ -18,6 +18,7 @@
 #include "rmse.cuh"
 #include "silhouette.cuh"
 #include "features.cuh"
+#include "hdbscan_mst.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -314,6 +315,23 @@ int llck_pool_features(const double* line_lists, int64_t ll_stride, const int32_
     if (!line_lists || !n_rows || !offset || !samples || !features || batch < 1 || ll_stride < 4 || !(dwell > 0.0)) return LLCK_E_BADARG;
     pool_features_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(line_lists, ll_stride, n_rows, (const long long*)offset, dwell, amplitude_tol,
                                                                    samples, features);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int llck_hdbscan_core_distances(const double* X, int32_t n, int32_t kmax, double* core, void* stream) {
+    if (!X || !core || n < 1 || kmax < 1 || kmax > HDB_KMAX || kmax > n) return LLCK_E_BADARG;
+    hdb_core_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(X, n, kmax, core);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32_t* core_row, int32_t nfits,
+                     double* min_reach, int32_t* cur_src, int64_t* mst_src, int64_t* mst_dst, double* mst_w, void* stream) {
+    if (!X || !core || !core_row || !min_reach || !cur_src || !mst_src || !mst_dst || !mst_w) return LLCK_E_BADARG;
+    if (n < 2 || n > HDB_PRIM_THREADS * 128 || nfits < 1) return LLCK_E_BADARG;
+    hdb_prim_kernel<<<nfits, HDB_PRIM_THREADS, 0, (cudaStream_t)stream>>>(X, n, core, core_row, min_reach, cur_src,
+                                                                          (long long*)mst_src, (long long*)mst_dst, mst_w);
     CK(cudaGetLastError());
     return 0;
 }

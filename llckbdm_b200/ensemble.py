@@ -194,6 +194,34 @@ def solve_pooled(signal, m, l, p, q, dwell, device=None, chunk=None, amplitude_t
     return (np.concatenate([pm[0] for pm in per_member]), np.concatenate([pm[1] for pm in per_member]), status)
 
 
+def hdbscan_msts_device(features, min_samples_list, device=None):
+    """Core distances (one brute-force pass for all k) and Prim spanning trees of the mutual-reachability graph for every
+    min_samples value at once (llck_hdbscan_core_distances / llck_hdbscan_mst), edge-for-edge what
+    sklearn.cluster._hdbscan._linkage.mst_from_data_matrix returns for the same points.
+
+    Returns (src int64 [F, n-1], dst int64 [F, n-1], w float64 [F, n-1])."""
+    torch = _require_cuda()
+    lib = _native.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    X = np.ascontiguousarray(features, dtype=np.float64)
+    n, F = X.shape[0], len(min_samples_list)
+    kmax = int(max(min_samples_list))
+    with torch.cuda.device(dev):
+        Xd = torch.from_numpy(X).to(dev)
+        core = torch.empty((kmax, n), dtype=torch.float64, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _native.check_rc(lib.llck_hdbscan_core_distances(Xd.data_ptr(), n, kmax, core.data_ptr(), st), "llck_hdbscan_core_distances")
+        rows = torch.tensor([int(k) - 1 for k in min_samples_list], dtype=torch.int32, device=dev)
+        mr = torch.empty((F, n), dtype=torch.float64, device=dev)
+        cs = torch.empty((F, n), dtype=torch.int32, device=dev)
+        src = torch.empty((F, n - 1), dtype=torch.int64, device=dev)
+        dst = torch.empty((F, n - 1), dtype=torch.int64, device=dev)
+        w = torch.empty((F, n - 1), dtype=torch.float64, device=dev)
+        _native.check_rc(lib.llck_hdbscan_mst(Xd.data_ptr(), n, core.data_ptr(), rows.data_ptr(), F, mr.data_ptr(), cs.data_ptr(),
+                                              src.data_ptr(), dst.data_ptr(), w.data_ptr(), st), "llck_hdbscan_mst")
+        return src.cpu().numpy(), dst.cpu().numpy(), w.cpu().numpy()
+
+
 def silhouette_samples_device(features, labelings, device=None):
     """Silhouette coefficient of every point for each labeling of the same points, on the device (llck_silhouette_batched;
     replaces sklearn.metrics.silhouette_samples as called at reference llckbdm.py:291).

@@ -4,8 +4,9 @@ The ensemble of KBDM solves (79 % of the reference's wall time)
 through ``sampling.sample_kbdm``.  Of the clustering stage ("next" row f-1 of the scope table) the two O(n^2)/O(M n K) loops
 are on the GPU too: the silhouette coefficients of all clusterings (one batched ``llck_silhouette_batched`` launch instead of
 M-1 ``sklearn.metrics.silhouette_samples`` calls, llckbdm.py:291) and the min-RMSE scoring of the cluster averages
-(``llck_rmse_batched``, llckbdm.py:120).  The HDBSCAN fits themselves stay on the host (third-party algorithm; label-for-label
-agreement is kept by calling the same clusterer) but run in parallel processes; pooling and cluster averaging are host numpy.
+(``llck_rmse_batched``, llckbdm.py:120), and so are the two O(n^2) stages of the HDBSCAN fits (core distances and Prim's spanning
+tree of the mutual-reachability graph, for all min_samples values in one launch each, edge-for-edge identical to the host
+clusterer's); the tree condensation / EOM selection stays the clusterer's own host code, so labels agree exactly.
 
 Clusterer: the reference imports the un-vendored ``hdbscan`` package (llckbdm.py:3).  If it is
 importable it is used; otherwise ``sklearn.cluster.HDBSCAN`` with the same defaults
@@ -19,7 +20,7 @@ import numpy as np
 from .metrics import calculate_freq_domain_rmse
 from .min_rmse_kbdm import min_rmse_kbdm
 from .sampling import filter_samples, sample_kbdm, sample_kbdm_pooled  # noqa: F401
-from .ensemble import silhouette_samples_device
+from .ensemble import hdbscan_msts_device, silhouette_samples_device
 from .sig_gen import gen_t_freq_arrays, multi_fid
 
 logger = logging.getLogger(__name__)
@@ -133,35 +134,85 @@ def _fit_one(features, min_samples):
     return np.asarray(model.labels_)
 
 
+def _labels_from_mst(src, dst, w):
+    """The host half of sklearn.cluster.HDBSCAN.fit after the spanning tree: sort the edges, single-linkage tree, condensed tree,
+    EOM selection (``_process_mst`` + ``tree_to_labels`` with the estimator's defaults)."""
+    from sklearn.cluster._hdbscan._linkage import MST_edge_dtype, make_single_linkage
+    from sklearn.cluster._hdbscan._tree import tree_to_labels
+    mst = np.empty(len(w), dtype=MST_edge_dtype)
+    mst["current_node"], mst["next_node"], mst["distance"] = src, dst, w
+    mst = mst[np.argsort(mst["distance"])]
+    ref = _HDBSCAN()
+    labels, _ = tree_to_labels(make_single_linkage(mst), ref.min_cluster_size, ref.cluster_selection_method,
+                               ref.allow_single_cluster, ref.cluster_selection_epsilon, ref.max_cluster_size)
+    return np.asarray(labels)
+
+
+def _gpu_fit_supported(features, min_samples_list):
+    """The device spanning trees reproduce sklearn's Euclidean Prim path edge for edge; anything else (the external ``hdbscan``
+    package, non-finite features, sizes outside the kernels' limits) keeps the plain host fits."""
+    if os.environ.get("LLCK_GPU_MST", "1") == "0" or not _HDBSCAN.__module__.startswith("sklearn."):
+        return False
+    n = len(features)
+    if n < 2 or n > 131072 or not min_samples_list or max(min_samples_list) > min(128, n) or min(min_samples_list) < 1:
+        return False
+    try:
+        from sklearn.cluster._hdbscan._linkage import MST_edge_dtype, make_single_linkage  # noqa: F401
+        from sklearn.cluster._hdbscan._tree import tree_to_labels  # noqa: F401
+    except Exception:  # noqa: BLE001
+        return False
+    return bool(np.isfinite(features).all())
+
+
 def _fit_all(features, min_samples_list):
-    """Labels of one HDBSCAN fit per min_samples value, in order.  Fits run in parallel host processes when there are enough
-    of them to pay for the process start-up (LLCK_CLUSTER_JOBS overrides the worker count; 1 = serial)."""
+    """Labels of one HDBSCAN fit per min_samples value, in order (reference llckbdm.py:104-116 + :280-283).
+
+    With sklearn's HDBSCAN as the clusterer the two O(n^2) stages of every fit -- k-nearest-neighbour core distances and Prim's
+    spanning tree of the mutual-reachability graph -- run on the device for all min_samples values at once
+    (``ensemble.hdbscan_msts_device``, edge lists identical to the host's), and only the O(n log n) tree condensation runs on the
+    host, spread over worker processes.  Otherwise the fits run on the host (in parallel processes when there are enough of them;
+    LLCK_CLUSTER_JOBS overrides the worker count, 1 = serial)."""
     n_fits = len(min_samples_list)
     jobs = int(os.environ.get("LLCK_CLUSTER_JOBS", "0")) or min(n_fits, os.cpu_count() or 1)
-    if jobs <= 1 or n_fits < 8 or len(features) < 4000:
+    parallel = jobs > 1 and n_fits >= 8 and len(features) >= 4000
+    if _gpu_fit_supported(features, min_samples_list):
+        src, dst, w = hdbscan_msts_device(features, min_samples_list)
+        if not parallel:
+            return [_labels_from_mst(src[f], dst[f], w[f]) for f in range(n_fits)]
+        from joblib import Parallel, delayed
+        return Parallel(n_jobs=jobs, prefer="processes")(delayed(_labels_from_mst)(src[f], dst[f], w[f]) for f in range(n_fits))
+    if not parallel:
         return [_fit_one(features, ms) for ms in min_samples_list]
     from joblib import Parallel, delayed
     return Parallel(n_jobs=jobs, prefer="processes")(delayed(_fit_one)(features, ms) for ms in min_samples_list)
 
 
 def _results_from_labelings(samples, features, labelings):
-    """ClusteringResult per labeling with >= 1 cluster (reference llckbdm.py:285-321), silhouettes from one device launch."""
-    keep = [lab for lab in labelings if len(set(lab.tolist()) - {-1}) > 0]
+    """ClusteringResult per labeling with >= 1 cluster (reference llckbdm.py:285-321), silhouettes from one device launch.
+    Clusters are grouped by one stable sort per labeling instead of one ``labels == k`` scan per cluster."""
+    keep = [np.asarray(lab) for lab in labelings if np.asarray(lab).max(initial=-1) >= 0]
     if not keep:
         return []
     sil_all = silhouette_samples_device(features, keep)
+    rates = samples.copy()
+    rates[:, 1] = 1 / rates[:, 1]                      # T2 is averaged as a rate (reference llckbdm.py:345-349)
     results = []
     for labels, sil in zip(keep, sil_all):
-        num_clusters = len(set(labels.tolist()) - {-1})
-        clustered, cluster_sil = [], []
-        for lab in range(num_clusters):
-            members = np.nonzero(labels == lab)
-            clustered.append(members)
-            cluster_sil.append(np.average(sil[members]))
+        num_clusters = int(labels.max()) + 1             # HDBSCAN labels are 0..k-1 (+ -1 for noise)
+        order = np.argsort(labels, kind="stable")        # ascending indices inside every cluster == np.nonzero(labels == k)
+        bounds = np.searchsorted(labels[order], np.arange(num_clusters + 1))
+        starts, counts = bounds[:-1], np.diff(bounds)
+        clustered = [(order[bounds[k]:bounds[k + 1]],) for k in range(num_clusters)]
+        if np.all(counts > 0):
+            cluster_sil = np.add.reduceat(sil[order], starts) / counts
+            summary = np.add.reduceat(rates[order], starts, axis=0) / counts[:, None]
+            summary[:, 1] = 1 / summary[:, 1]
+        else:                                            # not produced by HDBSCAN; keep the reference's per-cluster semantics
+            cluster_sil = np.array([np.average(sil[c]) for c in clustered])
+            summary = _summarize_clusters(samples=samples, clusters=clustered)
         results.append(ClusteringResult(num_clusters=num_clusters, labels=labels, clustered=clustered,
                                         non_clustered=np.nonzero(labels == -1),
-                                        summarized_line_list=_summarize_clusters(samples=samples, clusters=clustered),
-                                        clustered_silhouettes=np.array(cluster_sil)))
+                                        summarized_line_list=summary, clustered_silhouettes=np.asarray(cluster_sil)))
     return results
 
 

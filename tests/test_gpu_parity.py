@@ -196,6 +196,35 @@ def test_silhouette_kernel_matches_sklearn(cuda):
     assert got[2][-1] == 0.0
 
 
+def test_gpu_hdbscan_spanning_trees_give_identical_labels(cuda):
+    """Device core distances + Prim spanning trees (llck_hdbscan_core_distances / llck_hdbscan_mst) followed by the clusterer's own tree
+    condensation == sklearn.cluster.HDBSCAN(min_samples=k).fit(X).labels_, label for label, for every k; the edge lists equal
+    sklearn's mst_from_data_matrix bit for bit (duplicates and exact ties included)."""
+    from sklearn.cluster._hdbscan._linkage import mst_from_data_matrix
+    from sklearn.metrics import DistanceMetric
+    from sklearn.neighbors import NearestNeighbors
+    from llckbdm_b200 import llckbdm as L
+    from llckbdm_b200.ensemble import hdbscan_msts_device
+    rng = np.random.default_rng(4)
+    cent = rng.uniform(-1, 1, (20, 3))
+    X = np.concatenate([np.repeat(cent, 15, axis=0) + 1e-6 * rng.standard_normal((300, 3)), rng.uniform(-1, 1, (2100, 3))])
+    X = np.column_stack([X, np.zeros(len(X))])
+    X[7] = X[3]                                    # duplicate points: zero distances
+    X[100:110, :3] = np.round(X[100:110, :3], 1)   # coarse grid: exact distance ties
+    ks = [1, 2, 5, 9, 33]
+    src, dst, w = hdbscan_msts_device(X, ks)
+    for f, k in enumerate(ks):
+        cd = np.ascontiguousarray(NearestNeighbors(n_neighbors=k, algorithm="kd_tree").fit(X).kneighbors(X, k)[0][:, -1])
+        ref = mst_from_data_matrix(np.asarray(X, order="C"), cd, DistanceMetric.get_metric("euclidean"), 1.0)
+        assert np.array_equal(src[f], ref["current_node"]) and np.array_equal(dst[f], ref["next_node"])
+        assert np.array_equal(w[f], ref["distance"])
+        assert np.array_equal(L._labels_from_mst(src[f], dst[f], w[f]), L._fit_one(X, k))
+    assert L._gpu_fit_supported(X, ks)
+    got = L._fit_all(X, list(range(1, 12)))
+    for k, lab in zip(range(1, 12), got):
+        assert np.array_equal(lab, L._fit_one(X, k)), k
+
+
 def test_llc_kbdm_matches_host_clustering_stage(cuda):
     """llc_kbdm end to end (GPU solves, parallel fits, device silhouettes, device RMSE selection) == the same line lists pushed
     through a literal host restatement of reference llckbdm.py:93-141 (same clusterer, sklearn silhouettes, oracle RMSE)."""
