@@ -12,6 +12,8 @@ Hankel dimension m = 1024, l = m, p = 1, q = 0  (BASELINE.json: "KBDM solves/sec
   roofline  dominant kernel (hqr_kernel): algorithmic FP64 flops per launch / measured launch time
             vs the FP64 tensor (DMMA) peak measured on this pool (profiles/fp64_peak_r01.json -- MEASURED_PEAKS.json
             carries no FP64 figure)
+  llc_ensemble_c2  config C2 (100 truncations m in [700,1024]): solve-phase and end-to-end llc_kbdm latency
+  single_solve_c1  config C1: one kbdm() call, host to host
   cpu_baseline  the numpy/scipy restatement of the reference (oracle/, kind "port") timed on the host cores
 
 `--impl reference` times that CPU restatement alone (rank 0 only), one m = 1024 solve per step.
@@ -43,7 +45,7 @@ def parse():
     ap.add_argument("--m", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
-    ap.add_argument("--c2-full", action="store_true", help="also time llc_kbdm end to end on config C2 (HDBSCAN fits on the host cores: ~1 min)")
+    ap.add_argument("--no-c2-full", action="store_true", help="skip the end-to-end llc_kbdm timing of config C2 (solve + clustering, ~10 s)")
     return ap.parse_args()
 
 
@@ -306,13 +308,15 @@ def run_native(args):
             torch.cuda.synchronize()
             ts.append(time.perf_counter() - t0)
         out["single_solve_c1"] = {"m": m, "seconds": float(np.median(ts)), "note": "kbdm(data, dwell, m) host to host, median of 3"}
-    if rank == 0 and world == 1 and args.c2_full:
+    if rank == 0 and world == 1 and not args.no_c2 and not args.no_c2_full:
         from llckbdm_b200.llckbdm import llc_kbdm
         c = brain_sim(2048, SIGMA, 0)
         m2 = [700 + round(k * 324 / 99) for k in range(100)]
         t0 = time.perf_counter()
         r3 = llc_kbdm(c, DWELL, m2)
         out["llc_ensemble_c2"]["total_with_clustering_s"] = time.perf_counter() - t0
+        out["llc_ensemble_c2"]["note"] = ("solve_phase_s: host FID in, host line lists out; total_with_clustering_s: llc_kbdm end to end "
+                                          "(device solves, HDBSCAN spanning trees, silhouettes and RMSE selection; tree condensation on the host cores)")
         out["llc_ensemble_c2"]["clusters"] = int(len(r3.line_list))
         out["llc_ensemble_c2"]["host_cores"] = os.cpu_count()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
