@@ -42,6 +42,14 @@ def resolve_m_l(data_size, m, l, p):
     return int(m), int(l)
 
 
+def check_finite(data, m, p):
+    """The reference's scipy.linalg.svd / eig calls run with check_finite=True (kbdm.py:166,192): a NaN or Inf among the points the
+    Hankel matrices use, c[0 .. 2m+p-2], raises this ValueError there; same here, before anything is launched."""
+    used = np.asarray(data).ravel()[:2 * int(m) + int(p) - 1]
+    if not np.isfinite(used).all():
+        raise ValueError("array must not contain infs or NaNs")
+
+
 def raise_for_status(status, m=None):
     """Per-member numerical failure -> numpy.linalg.LinAlgError, like np.linalg.inv / scipy.linalg.eig would raise
     inside the reference (kbdm.py:186,192)."""
@@ -71,6 +79,7 @@ def kbdm(data, dwell, m=None, p=1, l=None, q=0):
     :return: (line_list float64[l,4] with columns (A, T2, F, PH), KbdmInfo)
     """
     m, l = resolve_m_l(data.size, m, l, p)
+    check_finite(data, m, p)
     if q > 0:
         logger.debug('Using Tikhonov Regularization with q=%f', q)
     res = solve_ensemble(np.asarray(data).ravel(), [m], [l], p, q, dwell)

@@ -6,7 +6,7 @@ import logging
 import numpy as np
 
 from .ensemble import solve_ensemble, solve_pooled
-from .kbdm import KbdmInfo, raise_for_status, resolve_m_l
+from .kbdm import KbdmInfo, check_finite, raise_for_status, resolve_m_l
 
 logger = logging.getLogger(__name__)
 
@@ -37,6 +37,7 @@ def sample_kbdm_scored(data, dwell, m_range, p, l, q=0, filter_invalid_features=
     for m in m_range:
         logger.info(f'Computing KBDM with m = {m}')
         mm, ll_ = resolve_m_l(data.size, m, l, p)
+        check_finite(data, mm, p)
         ms.append(mm)
         ls.append(ll_)
     if not ms:
@@ -65,6 +66,7 @@ def sample_kbdm_pooled(data, dwell, m_range, p, l, q=0):
     for m in m_range:
         logger.info(f'Computing KBDM with m = {m}')
         mm, ll_ = resolve_m_l(data.size, m, l, p)
+        check_finite(data, mm, p)
         ms.append(mm)
         ls.append(ll_)
     if not ms:

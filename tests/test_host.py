@@ -78,6 +78,17 @@ def test_resolve_m_l_matches_reference_validation():
         resolve_m_l(2048, 1024, None, 2)
 
 
+def test_non_finite_input_raises_like_scipy_check_finite():
+    from llckbdm_b200.kbdm import check_finite
+    c = np.ones(64, dtype=complex)
+    check_finite(c, 8, 1)
+    c[15] = np.nan                      # c[0 .. 2m+p-2] = c[0..15] is what the Hankel matrices use
+    with pytest.raises(ValueError, match="array must not contain infs or NaNs"):
+        check_finite(c, 8, 1)
+    c[15], c[16] = 1.0, np.inf          # beyond the used slice: the reference does not look at it
+    check_finite(c, 8, 1)
+
+
 def test_status_mapping():
     raise_for_status(0)
     for st in (1, 2, 3, 4):
