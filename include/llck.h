@@ -11,7 +11,8 @@
  * Conventions: plain pointers and sizes only; returns 0 on success, a negative cudaError_t on a CUDA
  * failure, or a positive LLCK_E_* code on bad arguments; never throws; allocates nothing (the caller
  * owns every buffer, including the workspace); all device work is issued on `stream`; the call
- * synchronises that stream (the Jacobi SVD polls a convergence counter once per sweep).
+ * synchronises that stream (it reads back how many members the divide-and-conquer SVD handed to the Jacobi
+ * fallback, and the Jacobi SVD polls a convergence counter once per sweep).
  * Per-member numerical failures are reported through status[] (the Python wrapper turns them into
  * numpy.linalg.LinAlgError like np.linalg.inv / scipy.linalg.eig would, kbdm.py:186,192).
  *
@@ -39,7 +40,7 @@ extern "C" {
 #define LLCK_STATUS_QR_NOCONV 1      /* Hessenberg-QR did not converge (scipy.linalg.eig -> LinAlgError) */
 #define LLCK_STATUS_SINGULAR 2       /* zero singular value among the l kept (np.linalg.inv -> LinAlgError, kbdm.py:186) */
 #define LLCK_STATUS_NONFINITE 3      /* non-finite pole or amplitude */
-#define LLCK_STATUS_SVD_NOCONV 4     /* Jacobi SVD hit the sweep limit */
+#define LLCK_STATUS_SVD_NOCONV 4     /* Jacobi SVD (fallback for rank-deficient members) hit the sweep limit */
 
 /* flags */
 #define LLCK_FLAG_DEBUG_KEEP 1       /* keep every intermediate in its own workspace matrix (tests only) */
@@ -68,11 +69,14 @@ size_t llck_debug_offset(int batch, int ld, int which);
  *   sing_vals  [dev]  float64 [batch][sv_stride]   all m[b] singular values, descending (kbdm.py:68,207)
  *   n_valid    [dev]  int32   [batch]              rows passing filter_samples (A>1e-6 and T2>0, sampling.py:92-95)
  *   status     [dev]  int32   [batch]              LLCK_STATUS_*
- *   info       [host] int32   [16] (optional)      [0]=Jacobi sweeps run, [1]=max QR multishift sweeps, [2]=ld, [3]=nbmax,
- *                                                  [4..12]=stage durations in us when LLCK_FLAG_TIMING (init, jacobi,
- *                                                  finalize+gather, T1+Ured, hessenberg, hqr, trevc, P+B+W, epilogue),
- *                                                  [13]=kernel launches issued, [14]=Jacobi rounds run,
- *                                                  [15]=average jacobi_update_kernel duration in us (LLCK_FLAG_TIMING)
+ *   info       [host] int32   [16] (optional)      [0]=Jacobi sweeps run (0 unless members fell back), [1]=max QR multishift sweeps,
+ *                                                  [2]=ld, [3]=nbmax, [4..12]=stage durations in us when LLCK_FLAG_TIMING (init +
+ *                                                  bidiagonalisation, SVD of the bidiagonal, back-multiplication, T1+Ured, hessenberg,
+ *                                                  hqr, trevc, P+B+W, epilogue), [13]=kernel launches issued, [14]=Jacobi rounds run,
+ *                                                  [15]=average jacobi_update_kernel duration in us (LLCK_FLAG_TIMING, fallback only)
+ * Workspace: llck_workspace_bytes(batch, ld, flags) = 11 ld x ld complex matrices per member (6 pipeline + 5 for the
+ * divide-and-conquer SVD of the bidiagonal) + panel / bookkeeping vectors.  Batches of <= 74 members run the one-CTA-per-member
+ * kernels as thread-block clusters of 2/4/8 CTAs per member.
  */
 int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int32_t* m, const int32_t* l,
                       int32_t p, double q, double dwell, int32_t batch,
