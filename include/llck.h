@@ -143,6 +143,12 @@ int llck_hdbscan_core_distances(const double* X, int32_t n, int32_t kmax, double
 int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32_t* core_row, int32_t nfits,
                      double* min_reach, int32_t* cur_src, int64_t* mst_src, int64_t* mst_dst, double* mst_w, void* stream);
 
+/* Batched FID synthesis -- llckbdm/sig_gen.py:57-71 (multi_fid) for `batch` parameter sets at once on t_n = n * dwell
+ * (the benchmark inputs of configs C4 / C5 and the residual model of llckbdm/llckbdm.py:177).
+ *   params  device float64 [batch][pstride], rows (A, T2, F, PH);  n_rows device int32 [batch];  out device complex128 [batch][N] */
+int llck_multi_fid_batched(const double* params, int64_t pstride, const int32_t* n_rows, int32_t batch, int32_t N, double dwell,
+                           void* out, void* stream);
+
 /* Stage entry (tests): divide-and-conquer SVD of `batch` real upper-bidiagonal matrices (second half of the replacement of
  * scipy.linalg.svd, llckbdm/kbdm.py:166).  d, e: device [batch][ld] (diagonal m, super-diagonal m-1); m: host [batch];
  * ld multiple of 64.  Outputs (device): sing_vals [batch][ld] descending, Us = U*diag(s) and V as complex128 [batch][ld*ld]

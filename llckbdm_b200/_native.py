@@ -24,6 +24,7 @@ SYMBOLS = (
     "llck_pool_features",
     "llck_hdbscan_core_distances",
     "llck_hdbscan_mst",
+    "llck_multi_fid_batched",
 )
 
 FLAG_DEBUG_KEEP = 1
@@ -88,6 +89,8 @@ def load():
     lib.llck_hdbscan_core_distances.argtypes = [c_vp, c_int, c_int, c_vp, c_vp]
     lib.llck_hdbscan_mst.restype = c_int
     lib.llck_hdbscan_mst.argtypes = [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.llck_multi_fid_batched.restype = c_int
+    lib.llck_multi_fid_batched.argtypes = [c_vp, c_i64, c_vp, c_int, c_int, c_dbl, c_vp, c_vp]
     _lib = lib
     return lib
 

@@ -336,6 +336,15 @@ int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32
     return 0;
 }
 
+int llck_multi_fid_batched(const double* params, int64_t pstride, const int32_t* n_rows, int32_t batch, int32_t N, double dwell,
+                           void* out, void* stream) {
+    if (!params || !n_rows || !out || batch < 1 || batch > 65535 || N < 1 || pstride < 4) return LLCK_E_BADARG;
+    dim3 grid((N + 255) / 256, batch);
+    multi_fid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, pstride, n_rows, N, dwell, (cplx*)out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int llck_bdc_test(const double* d, const double* e, const int32_t* m, int32_t batch, int32_t ld,
                   double* sing_vals, void* Us, void* V, int32_t* fallback, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

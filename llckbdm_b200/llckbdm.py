@@ -21,7 +21,7 @@ from .metrics import calculate_freq_domain_rmse
 from .min_rmse_kbdm import min_rmse_kbdm
 from .sampling import filter_samples, sample_kbdm, sample_kbdm_pooled  # noqa: F401
 from .ensemble import hdbscan_msts_device, silhouette_samples_device
-from .sig_gen import gen_t_freq_arrays, multi_fid
+from .sig_gen import gen_t_freq_arrays, multi_fid, multi_fid_batched_device  # noqa: F401
 
 logger = logging.getLogger(__name__)
 
@@ -96,7 +96,8 @@ def iterative_llc_kbdm(data, dwell, m_range, p=1, l=None, q=0.0, max_iterations=
             break
         keep = np.nonzero(res.silhouette > np.percentile(res.silhouette, thresholds[it]))
         line_list = res.line_list[keep]
-        estimate = estimate + multi_fid(t_array=t_array, params=line_list)
+        # residual model on the device (reference llckbdm.py:177 calls sig_gen.multi_fid on the host)
+        estimate = estimate + multi_fid_batched_device([line_list], len(data), dwell)[0].cpu().numpy()
         line_lists.append(line_list)
         silhouettes.append(res.silhouette[keep])
         n_peaks += len(line_list)

@@ -48,3 +48,37 @@ def lorentzian_peak(freq_array, a, t2, f, phase=0):
 def spec(freq_array, params):
     """Sum of Lorentzian peaks (reference sig_gen.py:124-137)."""
     return np.sum([lorentzian_peak(freq_array, *param) for param in params], axis=0)
+
+
+def multi_fid_batched_device(params, N, dwell, device=None):
+    """``multi_fid`` for many parameter sets at once on the GPU (llck_multi_fid_batched): ``params`` is a list of [K_b, 4] arrays
+    (or one [B, K, 4] array) of (amplitude, t2, frequency, phase) rows; returns a complex128 CUDA tensor [B, N] on
+    ``t = n * dwell`` (the grid of ``gen_t_freq_arrays``).  Rows are validated like ``fid`` does (sig_gen.py:140-169)."""
+    import torch
+    from . import _native
+    if not torch.cuda.is_available():
+        raise RuntimeError("llckbdm_b200 requires a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    sets = [np.asarray(p, dtype=np.float64).reshape(-1, 4) for p in params]
+    for ps in sets:
+        if (ps[:, 1] <= 0).any():
+            raise ValueError("T2 must be positive.")
+        if (ps[:, 0] < 0).any():
+            raise ValueError("Amplitude can't be negative.")
+    B = len(sets)
+    rows = np.array([len(ps) for ps in sets], dtype=np.int32)
+    kmax = max(1, int(rows.max())) if B else 1
+    packed = np.zeros((B, kmax, 4))
+    for i, ps in enumerate(sets):
+        packed[i, :len(ps)] = ps
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lib = _native.load()
+    with torch.cuda.device(dev):
+        out = torch.empty((B, int(N)), dtype=torch.complex128, device=dev)
+        for b0 in range(0, B, 65535):
+            b1 = min(B, b0 + 65535)
+            pd = torch.from_numpy(packed[b0:b1]).to(dev)
+            rd = torch.from_numpy(rows[b0:b1]).to(dev)
+            rc = lib.llck_multi_fid_batched(pd.data_ptr(), kmax * 4, rd.data_ptr(), b1 - b0, int(N), float(dwell),
+                                            out[b0:b1].data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _native.check_rc(rc, "llck_multi_fid_batched")
+    return out
