@@ -10,6 +10,7 @@
 //              and every A fragment is read from it as a sliding window.
 //              (reference: llckbdm/kbdm.py:95-130 builds the m x m matrices row by row on the host)
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 
 enum { A_NORMAL = 0, A_CONJT = 1, A_HANKEL = 2 };
@@ -246,6 +247,94 @@ __global__ void __launch_bounds__(256) zgemm_w32_kernel(GemmParams p) {
     }
 }
 
+// Rank-k update  C -= A * op(B)  with small K (<= KMAX = 32 or 64): the trailing / accumulation updates of the blocked
+// bidiagonalisation and Hessenberg reductions.  One 64x64 tile per CTA is latency bound here (two k-tiles of work between the
+// operand loads and the read-modify-write of C), so a CTA owns a 64-column block of C and streams through its row tiles:
+// op(B) stays in shared memory, the next A tile arrives by cp.async and the C fragments of the current tile are fetched into
+// registers before its DMMAs are issued, so every global latency is covered by tensor work.
+#define GR_LDA 66          // A tile: As[i + 66*k]      (= 2 mod 8)
+template <int KMAX, bool BCONJT>
+__global__ void __launch_bounds__(512, 1) zgemm_rankk_kernel(GemmParams p) {
+    constexpr int LDB = KMAX + 4;                        // B tile: Bs[k + LDB*j]  (= 4 mod 8)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* Bs = reinterpret_cast<cplx*>(smem_raw);
+    cplx* As[2] = {Bs + LDB * 64, Bs + LDB * 64 + GR_LDA * KMAX};
+    const int b = blockIdx.y;
+    const int M = (p.Mv ? p.Mv[b] : 0) + p.Mc, N = (p.Nv ? p.Nv[b] : 0) + p.Nc;
+    int K = (p.Kv ? p.Kv[b] : 0) + p.Kc;
+    if (p.Kcap > 0 && K > p.Kcap) K = p.Kcap;
+    const int col0 = blockIdx.x * 64;
+    if (M <= 0 || col0 >= N || K <= 0) return;
+    const int K4 = (K + 3) & ~3;                         // zero-filled up to a multiple of 4
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wr = warp >> 2, wc = warp & 3;             // 16 warps: warp tile 16 rows x 16 columns
+    const cplx* Ag = p.A + (long long)b * p.strideA;
+    const cplx* Bg = p.B + (long long)b * p.strideB;
+    cplx* Cg = p.C + (long long)b * p.strideC;
+    // op(B) block, once
+    for (int idx = tid; idx < 64 * KMAX; idx += 512) {
+        int k, j;
+        if (BCONJT) { j = idx & 63; k = idx >> 6; } else { k = idx % KMAX; j = idx / KMAX; }
+        const bool ok = (col0 + j < N) && (k < K);
+        const cplx* src = ok ? (BCONJT ? (Bg + (col0 + j) + (long long)p.ldb * k) : (Bg + k + (long long)p.ldb * (col0 + j))) : Bg;
+        cp_async16(&Bs[k + LDB * j], src, ok);
+    }
+    auto load_a = [&](int buf, int row0) {
+        for (int idx = tid; idx < 64 * KMAX; idx += 512) {
+            const int i = idx & 63, k = idx >> 6;
+            const bool ok = (row0 + i < M) && (k < K);
+            const cplx* src = ok ? (Ag + (row0 + i) + (long long)p.lda * k) : Ag;
+            cp_async16(&As[buf][i + GR_LDA * k], src, ok);
+        }
+        cp_async_commit();
+    };
+    const int ntiles = (M + 63) / 64;
+    load_a(0, 0);                                        // commits the B block together with the first A tile
+    for (int rt = 0; rt < ntiles; ++rt) {
+        const int buf = rt & 1, row0 = rt * 64;
+        if (rt + 1 < ntiles) load_a(buf ^ 1, row0 + 64);
+        // C fragments of this tile: issued now, consumed after the DMMAs
+        cplx cold[2][2][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = row0 + 16 * wr + 8 * i + g;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = col0 + 16 * wc + 8 * j + 2 * t;
+                cold[i][j][0] = (r < M && c < N) ? Cg[r + (long long)p.ldc * c] : mkc(0.0, 0.0);
+                cold[i][j][1] = (r < M && c + 1 < N) ? Cg[r + (long long)p.ldc * (c + 1)] : mkc(0.0, 0.0);
+            }
+        }
+        if (rt + 1 < ntiles) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+        double acc[2][2][4];
+        zero_acc<2, 2>(acc);
+        warp_zmma<2, 2, false, BCONJT>(acc, As[buf] + 16 * wr, 1, GR_LDA, Bs + LDB * (16 * wc), 1, LDB, K4);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = row0 + 16 * wr + 8 * i + g;
+            if (r >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = col0 + 16 * wc + 8 * j + 2 * t;
+                if (c < N) Cg[r + (long long)p.ldc * c] = mkc(cold[i][j][0].x - acc[i][j][0], cold[i][j][0].y - acc[i][j][2]);
+                if (c + 1 < N) Cg[r + (long long)p.ldc * (c + 1)] = mkc(cold[i][j][1].x - acc[i][j][1], cold[i][j][1].y - acc[i][j][3]);
+            }
+        }
+        __syncthreads();                                 // As[buf] is refilled two iterations ahead
+    }
+}
+
+template <int KMAX, bool BCONJT>
+static inline cudaError_t zgemm_rankk_launch(const GemmParams& p, int Nmax, int batch, cudaStream_t stream) {
+    const size_t smem = (size_t)((KMAX + 4) * 64 + 2 * GR_LDA * KMAX) * sizeof(cplx);
+    cudaError_t e = cudaFuncSetAttribute(zgemm_rankk_kernel<KMAX, BCONJT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((Nmax + 63) / 64, batch);
+    zgemm_rankk_kernel<KMAX, BCONJT><<<grid, 512, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
 static inline size_t zgemm_smem_bytes(int amode, int Kmax) {
     if (amode == A_HANKEL) return (size_t)(2 * G_B_ELEMS + G_SIG_MAX) * sizeof(cplx);
     return (size_t)(2 * G_A_ELEMS + 2 * G_B_ELEMS) * sizeof(cplx);
@@ -265,6 +354,10 @@ static inline cudaError_t zgemm_batched(int amode, const GemmParams& p, int Mmax
     if (batch <= 0 || Mmax <= 0 || Nmax <= 0 || Kmax <= 0) return cudaSuccess;
     dim3 grid((Mmax + G_BM - 1) / G_BM, (Nmax + G_BN - 1) / G_BN, batch);
     size_t smem = zgemm_smem_bytes(amode, Kmax);
+    if (amode == A_NORMAL && !breal && p.accum && !p.triB && Kmax <= 64 && batch <= 65535 && !getenv("LLCK_NO_RANKK")) {
+        if (Kmax <= 32) return bconjt ? zgemm_rankk_launch<32, true>(p, Nmax, batch, stream) : zgemm_rankk_launch<32, false>(p, Nmax, batch, stream);
+        return bconjt ? zgemm_rankk_launch<64, true>(p, Nmax, batch, stream) : zgemm_rankk_launch<64, false>(p, Nmax, batch, stream);
+    }
     if (amode == A_NORMAL && breal) return zgemm_launch<A_NORMAL, false, true>(p, grid, smem, stream);
     if (amode == A_NORMAL) return bconjt ? zgemm_launch<A_NORMAL, true>(p, grid, smem, stream) : zgemm_launch<A_NORMAL, false>(p, grid, smem, stream);
     if (amode == A_CONJT && Mmax <= 32 && !p.accum && !p.triB) {
