@@ -253,34 +253,38 @@ __global__ void __launch_bounds__(256) zgemm_w32_kernel(GemmParams p) {
 // op(B) stays in shared memory, the next A tile arrives by cp.async and the C fragments of the current tile are fetched into
 // registers before its DMMAs are issued, so every global latency is covered by tensor work.
 #define GR_LDA 66          // A tile: As[i + 66*k]      (= 2 mod 8)
-template <int KMAX, bool BCONJT>
-__global__ void __launch_bounds__(512, 1) zgemm_rankk_kernel(GemmParams p) {
+// GR_BN columns per CTA, 16 x 16 warp tiles: BN = 64 -> 16 warps, one CTA per SM; BN = 32 -> 8 warps, two CTAs per SM whose
+// epilogues (C read-modify-write) overlap each other's DMMAs.
+template <int KMAX, bool BCONJT, int BN>
+__global__ void __launch_bounds__(BN * 8, 64 / BN) zgemm_rankk_kernel(GemmParams p) {
     constexpr int LDB = KMAX + 4;                        // B tile: Bs[k + LDB*j]  (= 4 mod 8)
+    constexpr int NT_ = BN * 8;                          // threads
+    constexpr int WC = BN / 16;                          // warps across the columns
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* Bs = reinterpret_cast<cplx*>(smem_raw);
-    cplx* As[2] = {Bs + LDB * 64, Bs + LDB * 64 + GR_LDA * KMAX};
+    cplx* As[2] = {Bs + LDB * BN, Bs + LDB * BN + GR_LDA * KMAX};
     const int b = blockIdx.y;
     const int M = (p.Mv ? p.Mv[b] : 0) + p.Mc, N = (p.Nv ? p.Nv[b] : 0) + p.Nc;
     int K = (p.Kv ? p.Kv[b] : 0) + p.Kc;
     if (p.Kcap > 0 && K > p.Kcap) K = p.Kcap;
-    const int col0 = blockIdx.x * 64;
+    const int col0 = blockIdx.x * BN;
     if (M <= 0 || col0 >= N || K <= 0) return;
     const int K4 = (K + 3) & ~3;                         // zero-filled up to a multiple of 4
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int wr = warp >> 2, wc = warp & 3;             // 16 warps: warp tile 16 rows x 16 columns
+    const int wr = warp / WC, wc = warp % WC;            // warp tile: 16 rows x 16 columns
     const cplx* Ag = p.A + (long long)b * p.strideA;
     const cplx* Bg = p.B + (long long)b * p.strideB;
     cplx* Cg = p.C + (long long)b * p.strideC;
     // op(B) block, once
-    for (int idx = tid; idx < 64 * KMAX; idx += 512) {
+    for (int idx = tid; idx < BN * KMAX; idx += NT_) {
         int k, j;
-        if (BCONJT) { j = idx & 63; k = idx >> 6; } else { k = idx % KMAX; j = idx / KMAX; }
+        if (BCONJT) { j = idx % BN; k = idx / BN; } else { k = idx % KMAX; j = idx / KMAX; }
         const bool ok = (col0 + j < N) && (k < K);
         const cplx* src = ok ? (BCONJT ? (Bg + (col0 + j) + (long long)p.ldb * k) : (Bg + k + (long long)p.ldb * (col0 + j))) : Bg;
         cp_async16(&Bs[k + LDB * j], src, ok);
     }
     auto load_a = [&](int buf, int row0) {
-        for (int idx = tid; idx < 64 * KMAX; idx += 512) {
+        for (int idx = tid; idx < 64 * KMAX; idx += NT_) {
             const int i = idx & 63, k = idx >> 6;
             const bool ok = (row0 + i < M) && (k < K);
             const cplx* src = ok ? (Ag + (row0 + i) + (long long)p.lda * k) : Ag;
@@ -327,11 +331,21 @@ __global__ void __launch_bounds__(512, 1) zgemm_rankk_kernel(GemmParams p) {
 
 template <int KMAX, bool BCONJT>
 static inline cudaError_t zgemm_rankk_launch(const GemmParams& p, int Nmax, int batch, cudaStream_t stream) {
+    // K <= 32: 32-column blocks, two CTAs per SM (measured 90.5 vs 89.3 solves/s); K = 64 does not fit twice in shared memory
+    static const bool narrow = (KMAX <= 32) && getenv("LLCK_RANKK_BN64") == nullptr;
+    if (narrow) {
+        const size_t smem = (size_t)((KMAX + 4) * 32 + 2 * GR_LDA * KMAX) * sizeof(cplx);
+        cudaError_t e = cudaFuncSetAttribute(zgemm_rankk_kernel<KMAX, BCONJT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        dim3 grid((Nmax + 31) / 32, batch);
+        zgemm_rankk_kernel<KMAX, BCONJT, 32><<<grid, 256, smem, stream>>>(p);
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)((KMAX + 4) * 64 + 2 * GR_LDA * KMAX) * sizeof(cplx);
-    cudaError_t e = cudaFuncSetAttribute(zgemm_rankk_kernel<KMAX, BCONJT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(zgemm_rankk_kernel<KMAX, BCONJT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((Nmax + 63) / 64, batch);
-    zgemm_rankk_kernel<KMAX, BCONJT><<<grid, 512, smem, stream>>>(p);
+    zgemm_rankk_kernel<KMAX, BCONJT, 64><<<grid, 512, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
