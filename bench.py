@@ -270,8 +270,8 @@ def run_native(args):
         "roofline": {"bound": "tensor", "kernel": "hqr_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (148 members, m=1024) from the ncu --set full capture
-                     # summarised in profiles/r01f_ncu_summary.md (558.0 GB read + 539.6 GB written); None for other shapes
-                     "traffic": 1.0976e12 if (batch == 148 and m == 1024) else None, "traffic_unit": "B/launch", "peak_source": peak_src,
+                     # summarised in profiles/r01t_ncu_summary.md (561.3 GB read + 547.1 GB written); None for other shapes
+                     "traffic": 1.1084e12 if (batch == 148 and m == 1024) else None, "traffic_unit": "B/launch", "peak_source": peak_src,
                      "launches": int(args.steps), "avg_launch_ms": hqr_s * 1e3,
                      "algorithmic_flops_per_launch": flops_per_launch},
         "roofline_secondary": {"bound": "tensor", "kernel": "zgemm_batched_kernel<A_HANKEL> + <A_CONJT> (T1, Ured)",
