@@ -138,3 +138,40 @@ def test_sig_gen_and_metrics():
         sig_gen.fid(t, -1.0, 1.0, 1.0)
     peak = sig_gen.lorentzian_peak(f, 1.0, 0.1, 100.0)
     assert abs(f[np.argmax(peak.real)] - 100.0) < 1.0
+
+
+def test_labels_from_mst_reproduces_hdbscan_fit():
+    """Host half of the device-accelerated HDBSCAN fits: feeding the clusterer's OWN spanning tree (sklearn's Prim) through
+    llckbdm._labels_from_mst must reproduce HDBSCAN(min_samples=k).fit(X).labels_ exactly (the GPU test checks that the device
+    spanning trees equal sklearn's edge for edge)."""
+    from sklearn.cluster._hdbscan._linkage import mst_from_data_matrix
+    from sklearn.metrics import DistanceMetric
+    from sklearn.neighbors import NearestNeighbors
+    from llckbdm_b200 import llckbdm as L
+    rng = np.random.default_rng(1)
+    cent = rng.uniform(-1, 1, (8, 3))
+    X = np.concatenate([np.repeat(cent, 10, axis=0) + 1e-5 * rng.standard_normal((80, 3)), rng.uniform(-1, 1, (300, 3))])
+    X = np.column_stack([X, np.zeros(len(X))])
+    for k in (1, 4, 11):
+        cd = np.ascontiguousarray(NearestNeighbors(n_neighbors=k, algorithm="kd_tree").fit(X).kneighbors(X, k)[0][:, -1])
+        mst = mst_from_data_matrix(np.asarray(X, order="C"), cd, DistanceMetric.get_metric("euclidean"), 1.0)
+        got = L._labels_from_mst(mst["current_node"], mst["next_node"], mst["distance"])
+        assert np.array_equal(got, L._fit_one(X, k))
+
+
+def test_cluster_grouping_matches_reference_semantics(monkeypatch):
+    """_results_from_labelings (one stable sort per labeling) == the reference's per-cluster np.nonzero / np.average loops
+    (llckbdm.py:297-313, 324-353); the device silhouettes are replaced by a fixed array here."""
+    from llckbdm_b200 import llckbdm as L
+    rng = np.random.default_rng(0)
+    n = 3000
+    samples = np.column_stack([rng.random(n) + 0.1, rng.random(n) * 0.1 + 0.01, rng.uniform(-500, 500, n), rng.uniform(-1, 1, n)])
+    labels = rng.integers(-1, 25, n)
+    sil = rng.uniform(-1, 1, n)
+    monkeypatch.setattr(L, "silhouette_samples_device", lambda feats, labelings: np.array([sil for _ in labelings]))
+    res = L._results_from_labelings(samples, samples, [labels, np.full(n, -1)])
+    assert len(res) == 1 and res[0].num_clusters == 25
+    clusters = [np.nonzero(labels == k) for k in range(25)]
+    assert all(np.array_equal(a[0], b[0]) for a, b in zip(res[0].clustered, clusters))
+    assert np.allclose(res[0].summarized_line_list, L._summarize_clusters(samples, clusters), rtol=1e-13, atol=0)
+    assert np.allclose(res[0].clustered_silhouettes, [np.average(sil[c]) for c in clusters], rtol=1e-13, atol=1e-16)
