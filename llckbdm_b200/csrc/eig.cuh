@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
         return;
     }
     cplx* Tb = Tws + (long long)b * tstride + (long long)(k0 / HB_NB) * HB_NB * HB_NB;
+    // Rows 0..k0 of Y and of the panel's columns take no part in the panel factorisation (LAPACK zlahr2): the kernel works on rows
+    // >= r0 only, which cuts the level-2 traffic from n(n-c) to (n-k0)(n-c) per column; the caller fills Y[0:r0, :] = A[0:r0, r0:] (V T)
+    // and updates A[0:r0, r0:e] with two DMMA GEMMs afterwards.
+    const int r0 = k0 + 1;
 
     for (int idx = tid; idx < HB_NB * HB_NB; idx += E_THREADS) Tsm[idx] = mkc(0.0, 0.0);
     for (int idx = tid; idx < ld * HB_NB; idx += E_THREADS) { Vb[idx] = mkc(0.0, 0.0); Yb[idx] = mkc(0.0, 0.0); }
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
         // ---- b = A[:,c] - Y[:, :j] conj(V[c, :j]) ----
         if (tid < j) vrow[tid] = cconj(Vb[c + (long long)ld * tid]);
         __syncthreads();
-        for (int i = tid; i < n; i += E_THREADS) {
+        for (int i = r0 + tid; i < n; i += E_THREADS) {
             cplx acc = colc[i];
             for (int jj = 0; jj < j; ++jj) acc = csub(acc, cmul(Yb[i + (long long)ld * jj], vrow[jj]));
             bvec[i] = acc;
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
         if (c + 2 >= n) {
             // last two columns of the matrix: no reflector, just store the updated column
             cluster_barrier(csize);             // every CTA of the cluster has read the old column before anyone overwrites it
-            for (int i = tid; i < n; i += E_THREADS) colc[i] = bvec[i];
+            for (int i = r0 + tid; i < n; i += E_THREADS) colc[i] = bvec[i];
             __syncthreads();
             continue;
         }
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
             scale = cdiv(mkc(1.0, 0.0), mkc(alpha.x - beta, alpha.y));
         }
         __syncthreads();
-        for (int i = tid; i < n; i += E_THREADS) {
+        for (int i = r0 + tid; i < n; i += E_THREADS) {
             cplx vv = mkc(0.0, 0.0), hv = bvec[i];
             if (i == c + 1) { vv = mkc(1.0, 0.0); hv = trivial ? alpha : mkc(beta, 0.0); }
             else if (i > c + 1) { vv = trivial ? mkc(0.0, 0.0) : cmul(bvec[i], scale); hv = vv; }
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
             const int len = n - c - 1;
             const int q0 = (int)(((long long)len * crank) / csize), q1 = (int)(((long long)len * (crank + 1)) / csize);
             cplx* mine = (csize > 1) ? ypb + ((long long)(j & 1) * csize + crank) * ld : nullptr;
-            for (int i = tid; i < n; i += E_THREADS) {
+            for (int i = r0 + tid; i < n; i += E_THREADS) {
                 const cplx* row = Hb + i + (long long)ld * (c + 1);
                 const cplx* vv = vvec + (c + 1);
                 cplx y0 = mkc(0.0, 0.0), y1 = mkc(0.0, 0.0), y2 = mkc(0.0, 0.0), y3 = mkc(0.0, 0.0);
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long 
             if (csize > 1) {
                 cluster_barrier(csize);
                 const cplx* parts = ypb + (long long)(j & 1) * csize * ld;
-                for (int i = tid; i < n; i += E_THREADS) {
+                for (int i = r0 + tid; i < n; i += E_THREADS) {
                     cplx y = parts[i];
                     for (int r = 1; r < csize; ++r) y = cadd(y, parts[(long long)r * ld + i]);
                     for (int jj = 0; jj < j; ++jj) y = csub(y, cmul(Yb[i + (long long)ld * jj], zv[jj]));

@@ -787,6 +787,21 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
                 CK(launch_clustered(hess_panel_kernel, batch, hp_csize, E_THREADS, sm, st, bH, stride, ld, d_lv, k0, Vp, Yp, VTp, pstride, Tws, pstride,
                                     (cplx*)(ws + L.ypart), hp_csize));
                 const int e = k0 + HB_NB;
+                const int r0 = k0 + 1;
+                // rows 0..k0 were left out of the panel kernel:  Y[0:r0, :] = A[0:r0, r0:] * (V T)[r0:, :]
+                hp = gemm_params_zero();
+                hp.A = bH + (long long)ld * r0; hp.strideA = stride; hp.lda = ld;
+                hp.B = VTp + r0; hp.strideB = pstride; hp.ldb = ld;
+                hp.C = Yp; hp.strideC = pstride; hp.ldc = ld;
+                hp.Mc = r0; hp.Nc = HB_NB; hp.Kv = d_lv; hp.Kc = -r0;
+                CK(zgemm_batched(A_NORMAL, hp, r0, HB_NB, lmax - r0, batch, st));
+                // ... and the panel's own columns above the panel:  A[0:r0, r0:e] -= Y[0:r0, :] * V[r0:e, :]^H
+                hp = gemm_params_zero();
+                hp.A = Yp; hp.strideA = pstride; hp.lda = ld;
+                hp.B = Vp + r0; hp.strideB = pstride; hp.ldb = ld;
+                hp.C = bH + (long long)ld * r0; hp.strideC = stride; hp.ldc = ld;
+                hp.Mc = r0; hp.Nc = HB_NB - 1; hp.Kc = HB_NB; hp.accum = 1;
+                CK(zgemm_batched(A_NORMAL, hp, r0, HB_NB - 1, HB_NB, batch, st, true));
                 if (e >= lmax) continue;
                 // A[:, e:] -= Y * V[e:, :]^H
                 hp = gemm_params_zero();
