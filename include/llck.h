@@ -9,10 +9,14 @@
  *                       llckbdm/sampling.py:52-70 (sample_kbdm) becomes ONE call.
  *
  * Conventions: plain pointers and sizes only; returns 0 on success, a negative cudaError_t on a CUDA
- * failure, or a positive LLCK_E_* code on bad arguments; never throws; allocates nothing (the caller
- * owns every buffer, including the workspace); all device work is issued on `stream`; the call
- * synchronises that stream (it reads back how many members the divide-and-conquer SVD handed to the Jacobi
- * fallback, and the Jacobi SVD polls a convergence counter once per sweep).
+ * failure, or a positive LLCK_E_* code on bad arguments; never throws; allocates no device memory (the
+ * caller owns every buffer, including the workspace); all device work is issued on `stream` and the
+ * calls are STREAM-ORDERED AND ASYNCHRONOUS: they return as soon as the work is enqueued and never
+ * wait for the stream (exceptions, documented at the entry: LLCK_FLAG_TIMING and the *_test stage
+ * entries).  Every data-dependent decision (which members need the Jacobi SVD, Jacobi convergence,
+ * QR deflation) is taken on the device.  Host arrays passed to a call (m, l, sig_offset, sig_len) are
+ * staged before the call returns and may be reused at once.  No environment variable or other
+ * hidden state changes the behaviour of the library: every knob is an explicit argument (flags, llck_options).
  * Per-member numerical failures are reported through status[] (the Python wrapper turns them into
  * numpy.linalg.LinAlgError like np.linalg.inv / scipy.linalg.eig would, kbdm.py:186,192).
  *
@@ -29,11 +33,16 @@
 extern "C" {
 #endif
 
-#define LLCK_VERSION 100
+#define LLCK_VERSION 200
 
-/* argument errors */
+/* argument errors (positive return values) */
 #define LLCK_E_BADARG 1
-#define LLCK_E_WORKSPACE 2
+#define LLCK_E_WORKSPACE 2           /* workspace_bytes < llck_workspace_bytes(batch, ld, flags) */
+#define LLCK_E_SHORT_SIGNAL 3        /* sig_len[b] < 2 m[b] + p - 1: the Hankel matrices would read past the member's FID (kbdm.py:59-62) */
+#define LLCK_E_TOO_LARGE 4           /* max m > LLCK_M_MAX (llck_kbdm_batched) */
+
+/* largest supported Hankel dimension (the panel kernels keep 2 vectors of the leading dimension in shared memory) */
+#define LLCK_M_MAX 2048
 
 /* per-member status[] values */
 #define LLCK_STATUS_OK 0
@@ -44,7 +53,25 @@ extern "C" {
 
 /* flags */
 #define LLCK_FLAG_DEBUG_KEEP 1       /* keep every intermediate in its own workspace matrix (tests only) */
-#define LLCK_FLAG_TIMING 2           /* record CUDA events between stages; durations (us) returned in info[4..12] */
+#define LLCK_FLAG_TIMING 2           /* diagnostic: record CUDA events between stages, WAIT for the stream, return stage durations (us)
+                                        in info[4..12] and the maximum number of QR sweeps in info[1] */
+
+/* SVD back end for the real bidiagonal (llck_options.svd_mode) */
+#define LLCK_SVD_DC 0                /* divide and conquer; members it flags as numerically rank deficient fall back to Jacobi (default) */
+#define LLCK_SVD_JACOBI 1            /* block one-sided Jacobi for every member */
+
+/* Tuning knobs of llck_kbdm_batched.  Zero-initialise, set struct_size = sizeof(llck_options), change what you need; a NULL
+ * pointer means all defaults.  (Fields are only ever appended; struct_size tells the library which ones the caller knows.) */
+typedef struct llck_options {
+    int32_t struct_size;
+    int32_t svd_mode;            /* LLCK_SVD_* */
+    int32_t cluster_size;        /* CTAs per member of the one-CTA-per-member kernels for batches <= 74: 0 = auto, else 1, 2, 4 or 8 */
+    int32_t aed_window;          /* aggressive-early-deflation window of the multishift QR, 8..48; 0 = default (24) */
+    int32_t aed_nibble;          /* percent of the window that must deflate to skip the sweep (LAPACK NIBBLE); 0 = adaptive */
+    int32_t jacobi_max_sweeps;   /* sweeps enqueued for the Jacobi SVD (converged members exit at once); 0 = default (30) */
+    double  jacobi_conv;         /* scaled off-diagonal threshold that ends a member's Jacobi iteration; 0 = default (1e-6) */
+    void*   hqr_profile;         /* [dev] int64 [batch][10], optional: clock64 phase split of hqr_kernel per member (profiling) */
+} llck_options;
 
 int llck_version(void);
 
@@ -60,8 +87,10 @@ size_t llck_workspace_bytes(int batch, int ld, int flags);
  * 0:X(=L*S) 1:V 2:Rs 3:Lt 4:T1 5:Ured 6:Hhess 7:Qhess 8:T 9:Z 10:Xev 11:P 12:B 13:W */
 size_t llck_debug_offset(int batch, int ld, int which);
 
-/* Batched KBDM solve.  Member b uses the FID  signals[sig_offset[b] ... ]  (it reads 2*m[b]+p-1 points),
- * Hankel dimension m[b], kept rank l[b] (1 <= l <= m), shift p >= 1, Tikhonov q >= 0 (kbdm.py:19).
+/* Batched KBDM solve.  Member b uses the FID  signals[sig_offset[b] ... sig_offset[b] + sig_len[b])  (it reads the first
+ * 2*m[b]+p-1 points; a shorter FID is LLCK_E_SHORT_SIGNAL, nothing is launched), Hankel dimension m[b] <= LLCK_M_MAX, kept rank
+ * l[b] (1 <= l <= m), shift p >= 1, Tikhonov q >= 0 (kbdm.py:19).  signals [dev] complex; sig_offset, sig_len [host] int64 [batch]
+ * (in complex elements); m, l [host] int32 [batch] -- sizes stay on the host because they set the launch geometry.
  *
  *   line_lists [dev]  float64 [batch][ll_stride]   rows (A, T2, F, PH), l[b] rows per member, eig order (kbdm.py:88-92)
  *   mu_out     [dev]  complex [batch][mu_stride]   raw poles (optional, may be NULL)
@@ -69,26 +98,31 @@ size_t llck_debug_offset(int batch, int ld, int which);
  *   sing_vals  [dev]  float64 [batch][sv_stride]   all m[b] singular values, descending (kbdm.py:68,207)
  *   n_valid    [dev]  int32   [batch]              rows passing filter_samples (A>1e-6 and T2>0, sampling.py:92-95)
  *   status     [dev]  int32   [batch]              LLCK_STATUS_*
- *   info       [host] int32   [16] (optional)      [0]=Jacobi sweeps run (0 unless members fell back), [1]=max QR multishift sweeps,
- *                                                  [2]=ld, [3]=nbmax, [4..12]=stage durations in us when LLCK_FLAG_TIMING (init +
- *                                                  bidiagonalisation, SVD of the bidiagonal, back-multiplication, T1+Ured, hessenberg,
- *                                                  hqr, trevc, P+B+W, epilogue), [13]=kernel launches issued, [14]=Jacobi rounds run,
- *                                                  [15]=average jacobi_update_kernel duration in us (LLCK_FLAG_TIMING, fallback only)
+ *   opts       [host] llck_options (optional, NULL = defaults)
+ *   info       [host] int32   [16] (optional)      [2]=ld, [3]=Jacobi column blocks of the largest member, [13]=kernels enqueued by
+ *                                                  this call (counted at the launch sites), [14]=Jacobi rounds enqueued; with
+ *                                                  LLCK_FLAG_TIMING also [1]=max QR multishift sweeps and [4..12]=stage durations in us
+ *                                                  (init + bidiagonalisation, SVD of the bidiagonal, back-multiplication, T1+Ured,
+ *                                                  hessenberg, hqr, trevc, P+B+W, epilogue)
  * Workspace: llck_workspace_bytes(batch, ld, flags) = 11 ld x ld complex matrices per member (6 pipeline + 5 for the
  * divide-and-conquer SVD of the bidiagonal) + panel / bookkeeping vectors.  Batches of <= 74 members run the one-CTA-per-member
  * kernels as thread-block clusters of 2/4/8 CTAs per member.
+ * Asynchronous: returns once the launch sequence is enqueued on `stream` (LLCK_FLAG_TIMING makes it wait).  The Jacobi fallback
+ * is enqueued unconditionally -- llck_options.jacobi_max_sweeps sweeps whose CTAs exit at once for members the divide-and-conquer
+ * SVD solved -- so that no decision needs a device-to-host read-back.
  */
-int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int32_t* m, const int32_t* l,
+int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int64_t* sig_len, const int32_t* m, const int32_t* l,
                       int32_t p, double q, double dwell, int32_t batch,
                       double* line_lists, int64_t ll_stride,
                       void* mu_out, void* d_out, int64_t mu_stride,
                       double* sing_vals, int64_t sv_stride,
                       int32_t* n_valid, int32_t* status,
-                      void* workspace, size_t workspace_bytes, int32_t flags,
+                      void* workspace, size_t workspace_bytes, int32_t flags, const llck_options* opts,
                       void* stream, int32_t* info);
 
 /* Stage-level entry (tests / profiling): one complex GEMM  C = opA(A) * B  through the production kernel.
- * amode: 0 normal, 1 conj-transpose (A stored K x M), 2 implicit Hankel (A[i,k] = sig[i+k+shift]). All [dev]. */
+ * amode: 0 normal, 1 conj-transpose (A stored K x M), 2 implicit Hankel (A[i,k] = sig[i+k+shift]). All [dev].
+ * Test helper: allocates two small device scratch arrays and waits for the stream. */
 int llck_zgemm(int32_t amode, const void* A, int32_t lda, const void* B, int32_t ldb, void* C, int32_t ldc,
                int32_t M, int32_t N, int32_t K, const void* sig, int32_t shift, void* stream);
 
@@ -104,7 +138,8 @@ int llck_bidiag_test(void* A, int32_t m, int32_t ld, double* d_out, double* e_ou
  *   line_lists  device float64 [batch][ll_stride], rows (A, T2, F, PH) as written by llck_kbdm_batched
  *   n_rows      device int32 [batch]: rows of each candidate
  *   filter      1: skip rows failing  A > amplitude_tol and T2 > 0  (filter_samples, llckbdm/sampling.py:75-97)
- *   rmse_out    device float64 [batch]; +inf for a candidate without valid rows (min_rmse_kbdm.py:36-37)            */
+ *   rmse_out    device float64 [batch]; +inf for a candidate without valid rows (min_rmse_kbdm.py:36-37)
+ * Any N: FIDs of up to 12800 points keep the whole model in shared memory, longer ones are tiled over n.             */
 int llck_rmse_batched(const void* data, int32_t N, double dwell, const double* line_lists, int64_t ll_stride,
                       const int32_t* n_rows, int32_t batch, int32_t filter, double amplitude_tol, double* rmse_out, void* stream);
 
@@ -142,6 +177,19 @@ int llck_pool_features(const double* line_lists, int64_t ll_stride, const int32_
 int llck_hdbscan_core_distances(const double* X, int32_t n, int32_t kmax, double* core, void* stream);
 int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32_t* core_row, int32_t nfits,
                      double* min_reach, int32_t* cur_src, int64_t* mst_src, int64_t* mst_dst, double* mst_w, void* stream);
+
+/* HOST function: flat cluster labels of `nfits` HDBSCAN fits from their spanning trees -- the rest of every fit of
+ * llckbdm/llckbdm.py:280-283 after the spanning tree (single-linkage dendrogram, condensed tree, stabilities, excess-of-mass
+ * selection, labelling) with the clusterer's defaults (min_cluster_size 5 -> pass 5, "eom", allow_single_cluster False,
+ * cluster_selection_epsilon 0).  Label for label what sklearn.cluster.HDBSCAN (the stand-in for the un-vendored `hdbscan`
+ * package) returns for the same sorted edges: rows and floating-point sums are formed in its order.  The fits run on
+ * `nthreads` host threads (0 = all hardware threads).  All pointers [host].
+ *   mst_src, mst_dst  int64 [nfits][n-1], mst_w float64 [nfits][n-1]: edges as written by llck_hdbscan_mst
+ *   order             int64 [nfits][n-1] (optional): permutation sorting each fit's edges by weight, ascending -- pass the
+ *                     clusterer's own argsort so that equal weights are processed in its order; NULL = already sorted
+ *   labels            int32 [nfits][n] out: 0..k-1, -1 = noise                                                              */
+int llck_hdbscan_labels(const int64_t* mst_src, const int64_t* mst_dst, const double* mst_w, const int64_t* order, int32_t n, int32_t nfits,
+                        int32_t min_cluster_size, int32_t nthreads, int32_t* labels);
 
 /* Batched FID synthesis -- llckbdm/sig_gen.py:57-71 (multi_fid) for `batch` parameter sets at once on t_n = n * dwell
  * (the benchmark inputs of configs C4 / C5 and the residual model of llckbdm/llckbdm.py:177).

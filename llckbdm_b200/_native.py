@@ -24,11 +24,32 @@ SYMBOLS = (
     "llck_pool_features",
     "llck_hdbscan_core_distances",
     "llck_hdbscan_mst",
+    "llck_hdbscan_labels",
     "llck_multi_fid_batched",
 )
 
 FLAG_DEBUG_KEEP = 1
 FLAG_TIMING = 2
+
+E_BADARG = 1
+E_WORKSPACE = 2
+E_SHORT_SIGNAL = 3
+E_TOO_LARGE = 4
+M_MAX = 2048
+
+SVD_DC = 0
+SVD_JACOBI = 1
+
+
+class Options(ctypes.Structure):
+    """``llck_options`` of include/llck.h: explicit tuning knobs of llck_kbdm_batched (the library reads no environment)."""
+    _fields_ = [("struct_size", ctypes.c_int32), ("svd_mode", ctypes.c_int32), ("cluster_size", ctypes.c_int32),
+                ("aed_window", ctypes.c_int32), ("aed_nibble", ctypes.c_int32), ("jacobi_max_sweeps", ctypes.c_int32),
+                ("jacobi_conv", ctypes.c_double), ("hqr_profile", ctypes.c_void_p)]
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.struct_size = ctypes.sizeof(Options)
 
 STATUS_OK = 0
 STATUS_QR_NOCONV = 1
@@ -64,13 +85,13 @@ def load():
     lib.llck_debug_offset.argtypes = [c_int, c_int, c_int]
     lib.llck_kbdm_batched.restype = c_int
     lib.llck_kbdm_batched.argtypes = [
-        c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+        c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
         c_int, c_dbl, c_dbl, c_int,
         c_vp, c_i64,
         c_vp, c_vp, c_i64,
         c_vp, c_i64,
         c_vp, c_vp,
-        c_vp, c_sz, c_int,
+        c_vp, c_sz, c_int, ctypes.POINTER(Options),
         c_vp, ctypes.POINTER(c_int),
     ]
     lib.llck_zgemm.restype = c_int
@@ -89,10 +110,20 @@ def load():
     lib.llck_hdbscan_core_distances.argtypes = [c_vp, c_int, c_int, c_vp, c_vp]
     lib.llck_hdbscan_mst.restype = c_int
     lib.llck_hdbscan_mst.argtypes = [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.llck_hdbscan_labels.restype = c_int
+    lib.llck_hdbscan_labels.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]
     lib.llck_multi_fid_batched.restype = c_int
     lib.llck_multi_fid_batched.argtypes = [c_vp, c_i64, c_vp, c_int, c_int, c_dbl, c_vp, c_vp]
     _lib = lib
     return lib
+
+
+_E_TEXT = {
+    E_BADARG: "bad argument",
+    E_WORKSPACE: "workspace too small",
+    E_SHORT_SIGNAL: "a member's signal is shorter than the 2m + p - 1 points its Hankel matrices use",
+    E_TOO_LARGE: f"Hankel dimension m above the supported maximum ({M_MAX})",
+}
 
 
 def check_rc(rc, what):
@@ -100,4 +131,4 @@ def check_rc(rc, what):
         return
     if rc < 0:
         raise RuntimeError(f"{what}: CUDA error {-rc}")
-    raise ValueError(f"{what}: bad argument (code {rc})")
+    raise ValueError(f"{what}: {_E_TEXT.get(rc, 'bad argument')} (code {rc})")

@@ -712,9 +712,11 @@ static int bdc_driver(BdcParams p, int mmax, cudaStream_t st) {
     if ((e = cudaMemsetAsync(p.Q[0], 0, sizeof(double) * (size_t)batch * p.qstride, st)) != cudaSuccess) return -(int)e;
     if ((e = cudaMemsetAsync(p.Q[1], 0, sizeof(double) * (size_t)batch * p.qstride, st)) != cudaSuccess) return -(int)e;
     bdc_init_kernel<<<batch, 256, 0, st>>>(p);
+    LLCK_LAUNCHED();
     {
         dim3 grid(nlmax, batch);
         bdc_leaf_kernel<<<grid, 32, 0, st>>>(p);
+        LLCK_LAUNCHED();
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return -(int)e;
     const int Nmax = 2 * mmax;
@@ -741,6 +743,7 @@ static int bdc_driver(BdcParams p, int mmax, cudaStream_t st) {
         bdc_gemm_kernel<<<g4, 256, 0, st>>>(p, tn);
         dim3 g5(64, merges, batch);
         bdc_copydefl_kernel<<<g5, 256, 0, st>>>(p);
+        llck_launch_count += 7;
         if ((e = cudaGetLastError()) != cudaSuccess) return -(int)e;
     }
     return 0;

@@ -7,6 +7,10 @@
 
 typedef double2 cplx;
 
+// kernels enqueued by the current llck_kbdm_batched call on this host thread (reported in info[13]); bumped at every launch site
+static thread_local int llck_launch_count = 0;
+#define LLCK_LAUNCHED() (++llck_launch_count)
+
 #define LLCK_EPS 2.220446049250313e-16
 #define LLCK_SAFMIN 2.2250738585072014e-308
 

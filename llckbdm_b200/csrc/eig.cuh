@@ -1,10 +1,11 @@
 // Batched complex-FP64 nonsymmetric eigensolver for the reduced operator U_red (l x l) -- replaces
 // scipy.linalg.eig / LAPACK zgeev at reference llckbdm/kbdm.py:192.  One CTA per ensemble member:
-//   hessenberg_kernel : Householder reduction H = Q^H U Q, then Q formed by backward accumulation
+//   hess_panel_kernel : blocked (compact-WY) Householder reduction H = Q^H U Q; trailing updates and the backward
+//                       accumulation of Q are batched DMMA GEMMs issued by the host driver
 //   hqr_kernel        : small-bulge multishift QR (single-shift complex bulges, spacing 2, chased in
 //                       lockstep by one warp each inside a 64x64 shared-memory window; the accumulated
 //                       unitary W is applied to the off-window strips of H and to Z with DMMA GEMMs)
-//   trevc_kernel      : eigenvectors of the triangular Schur factor by column-oriented back substitution
+//   trevc_diag_kernel : eigenvectors of the triangular Schur factor by block back substitution (+ one DMMA GEMM per block)
 // Eigenvector scale/phase is irrelevant downstream, so LAPACK's normalisation is not reproduced.
 #pragma once
 #include "common.cuh"
@@ -30,100 +31,6 @@ __device__ __forceinline__ void cluster_barrier(int csize) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Hessenberg reduction + Q formation
-// ---------------------------------------------------------------------------------------------
-// dynamic smem: ldmax * 16 (v) + 512 bytes
-__global__ void __launch_bounds__(E_THREADS, 1) hessenberg_kernel(cplx* H, cplx* Q, long long stride, int ld, const int* lv, cplx* tau_ws) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* v = reinterpret_cast<cplx*>(smem_raw);
-    double* red = reinterpret_cast<double*>(v + ld);
-    const int b = blockIdx.x, n = lv[b];
-    cplx* Hb = H + (long long)b * stride;
-    cplx* Qb = Q + (long long)b * stride;
-    cplx* tau_b = tau_ws + (long long)b * ld;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    for (int k = 0; k + 2 < n; ++k) {
-        const int len = n - k - 1;
-        cplx* colk = Hb + (long long)ld * k + (k + 1);
-        double part = 0.0;
-        for (int i = 1 + tid; i < len; i += E_THREADS) part += cabs2(colk[i]);
-        const double xnorm2 = block_sum(part, red);
-        const cplx alpha = colk[0];
-        if (xnorm2 == 0.0 && alpha.y == 0.0) {
-            if (tid == 0) tau_b[k] = mkc(0.0, 0.0);
-            __syncthreads();
-            continue;
-        }
-        const double beta = -copysign(sqrt(cabs2(alpha) + xnorm2), alpha.x);
-        const cplx tau = mkc((beta - alpha.x) / beta, -alpha.y / beta);
-        const cplx scale = cdiv(mkc(1.0, 0.0), mkc(alpha.x - beta, alpha.y));
-        __syncthreads();   // everyone has read alpha
-        for (int i = tid; i < len; i += E_THREADS) {
-            if (i == 0) { v[0] = mkc(1.0, 0.0); colk[0] = mkc(beta, 0.0); }
-            else { cplx vv = cmul(colk[i], scale); v[i] = vv; colk[i] = vv; }
-        }
-        if (tid == 0) tau_b[k] = tau;
-        __syncthreads();
-        // left: A[k+1:n, k+1:n] -= conj(tau) v (v^H A)
-        const cplx ctau = cconj(tau);
-        for (int j = k + 1 + warp; j < n; j += E_NWARPS) {
-            cplx* col = Hb + (long long)ld * j + (k + 1);
-            cplx d = mkc(0.0, 0.0);
-            for (int i = lane; i < len; i += 32) d = cfmac(v[i], col[i], d);
-            d = warp_sum(d);
-            const cplx f = cmul(ctau, d);
-            for (int i = lane; i < len; i += 32) col[i] = csub(col[i], cmul(f, v[i]));
-        }
-        __syncthreads();
-        // right: A[0:n, k+1:n] -= tau (A v) v^H
-        for (int i = tid; i < n; i += E_THREADS) {
-            cplx* row = Hb + i + (long long)ld * (k + 1);
-            cplx y0 = mkc(0.0, 0.0), y1 = mkc(0.0, 0.0);
-            int j = 0;
-            for (; j + 1 < len; j += 2) {
-                y0 = cfma(row[(long long)ld * j], v[j], y0);
-                y1 = cfma(row[(long long)ld * (j + 1)], v[j + 1], y1);
-            }
-            if (j < len) y0 = cfma(row[(long long)ld * j], v[j], y0);
-            const cplx ty = cmul(tau, cadd(y0, y1));
-            for (j = 0; j < len; ++j) {
-                cplx* e = row + (long long)ld * j;
-                *e = csub(*e, cmul(ty, cconj(v[j])));
-            }
-        }
-        __syncthreads();
-    }
-    // ---- Q = P_0 P_1 ... P_{n-3} by backward accumulation ----
-    for (long long idx = tid; idx < (long long)ld * n; idx += E_THREADS) {
-        int i = (int)(idx % ld), j = (int)(idx / ld);
-        Qb[idx] = mkc((i == j) ? 1.0 : 0.0, 0.0);
-    }
-    __syncthreads();
-    for (int k = n - 3; k >= 0; --k) {
-        const cplx tau = tau_b[k];
-        if (tau.x == 0.0 && tau.y == 0.0) continue;
-        const int len = n - k - 1;
-        const cplx* colk = Hb + (long long)ld * k + (k + 1);
-        for (int i = tid; i < len; i += E_THREADS) v[i] = (i == 0) ? mkc(1.0, 0.0) : colk[i];
-        __syncthreads();
-        for (int j = k + 1 + warp; j < n; j += E_NWARPS) {
-            cplx* col = Qb + (long long)ld * j + (k + 1);
-            cplx d = mkc(0.0, 0.0);
-            for (int i = lane; i < len; i += 32) d = cfmac(v[i], col[i], d);
-            d = warp_sum(d);
-            const cplx f = cmul(tau, d);
-            for (int i = lane; i < len; i += 32) col[i] = csub(col[i], cmul(f, v[i]));
-        }
-        __syncthreads();
-    }
-    // ---- clear the reflector storage below the subdiagonal ----
-    for (int j = warp; j + 2 < n; j += E_NWARPS) {
-        cplx* col = Hb + (long long)ld * j;
-        for (int i = j + 2 + lane; i < n; i += 32) col[i] = mkc(0.0, 0.0);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Blocked (compact-WY) Hessenberg reduction: panel kernel.
@@ -937,64 +844,6 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
         if (prof) { for (int i = 0; i < 10; ++i) prof[10 * b + i] = tp[i]; if (lane == 0) { prof[10 * b + 0] = aedprof[0]; prof[10 * b + 6] = aedprof[1]; } }
     }
 #undef PROF
-}
-
-// ---------------------------------------------------------------------------------------------
-// eigenvectors of upper-triangular T (in H storage): X upper triangular, T X = X diag(T)
-// dynamic smem: ld*16 (tcol) + ld*8 (smin) + 512
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(E_THREADS, 1) trevc_kernel(const cplx* Tm, cplx* X, long long stride, int ld, const int* lv) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* tcol = reinterpret_cast<cplx*>(smem_raw);
-    cplx* tdiag = tcol + ld;
-    double* red = reinterpret_cast<double*>(tdiag + ld);
-    const int b = blockIdx.x, n = lv[b];
-    const cplx* Tb = Tm + (long long)b * stride;
-    cplx* Xb = X + (long long)b * stride;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const double smlnum = LLCK_SAFMIN * ((double)n / LLCK_EPS);
-
-    for (int k = warp; k < n; k += E_NWARPS) {
-        const cplx* tc = Tb + (long long)ld * k;
-        cplx* xc = Xb + (long long)ld * k;
-        for (int i = lane; i < n; i += 32) xc[i] = (i < k) ? cneg(tc[i]) : mkc(i == k ? 1.0 : 0.0, 0.0);
-    }
-    for (int i = tid; i < n; i += E_THREADS) tdiag[i] = Tb[i + (long long)ld * i];
-    __syncthreads();
-    for (int j = n - 2; j >= 0; --j) {
-        const cplx tjj = tdiag[j];
-        // divisions on row j, and stage column j of T
-        for (int k = j + 1 + tid; k < n; k += E_THREADS) {
-            const cplx tkk = tdiag[k];
-            cplx d = csub(tjj, tkk);
-            const double smin = fmax(LLCK_EPS * cabs1(tkk), smlnum);
-            if (cabs1(d) < smin) d = mkc(smin, 0.0);
-            cplx* e = Xb + j + (long long)ld * k;
-            *e = cdiv(*e, d);
-        }
-        for (int i = tid; i < j; i += E_THREADS) tcol[i] = Tb[i + (long long)ld * j];
-        __syncthreads();
-        if (j > 0) {
-            for (int k = j + 1 + warp; k < n; k += E_NWARPS) {
-                cplx* xc = Xb + (long long)ld * k;
-                const cplx xjk = xc[j];
-                for (int i = lane; i < j; i += 32) xc[i] = csub(xc[i], cmul(xjk, tcol[i]));
-            }
-        }
-        __syncthreads();
-    }
-    // normalise each eigenvector to unit max-|.|_1 entry (keeps downstream products well scaled)
-    for (int k = warp; k < n; k += E_NWARPS) {
-        cplx* xc = Xb + (long long)ld * k;
-        double mx = 0.0;
-        for (int i = lane; i <= k; i += 32) mx = fmax(mx, cabs1(xc[i]));
-        mx = warp_max(mx);
-        if (mx > 0.0 && isfinite(mx)) {
-            const double sc = 1.0 / mx;
-            for (int i = lane; i <= k; i += 32) xc[i] = cscale(xc[i], sc);
-        }
-    }
-    (void)red;
 }
 
 // ---------------------------------------------------------------------------------------------

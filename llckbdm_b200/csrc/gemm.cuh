@@ -10,7 +10,6 @@
 //              and every A fragment is read from it as a sliding window.
 //              (reference: llckbdm/kbdm.py:95-130 builds the m x m matrices row by row on the host)
 #pragma once
-#include <stdlib.h>
 #include "common.cuh"
 
 enum { A_NORMAL = 0, A_CONJT = 1, A_HANKEL = 2 };
@@ -332,8 +331,8 @@ __global__ void __launch_bounds__(BN * 8, 64 / BN) zgemm_rankk_kernel(GemmParams
 template <int KMAX, bool BCONJT>
 static inline cudaError_t zgemm_rankk_launch(const GemmParams& p, int Nmax, int batch, cudaStream_t stream) {
     // K <= 32: 32-column blocks, two CTAs per SM (measured 90.5 vs 89.3 solves/s); K = 64 does not fit twice in shared memory
-    static const bool narrow = (KMAX <= 32) && getenv("LLCK_RANKK_BN64") == nullptr;
-    if (narrow) {
+    LLCK_LAUNCHED();
+    if (KMAX <= 32) {
         const size_t smem = (size_t)((KMAX + 4) * 32 + 2 * GR_LDA * KMAX) * sizeof(cplx);
         cudaError_t e = cudaFuncSetAttribute(zgemm_rankk_kernel<KMAX, BCONJT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -360,6 +359,7 @@ static inline cudaError_t zgemm_launch(const GemmParams& p, dim3 grid, size_t sm
     cudaError_t e = cudaFuncSetAttribute(zgemm_batched_kernel<AMODE, BCONJT, BREAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     zgemm_batched_kernel<AMODE, BCONJT, BREAL><<<grid, 256, smem, stream>>>(p);
+    LLCK_LAUNCHED();
     return cudaGetLastError();
 }
 
@@ -368,7 +368,7 @@ static inline cudaError_t zgemm_batched(int amode, const GemmParams& p, int Mmax
     if (batch <= 0 || Mmax <= 0 || Nmax <= 0 || Kmax <= 0) return cudaSuccess;
     dim3 grid((Mmax + G_BM - 1) / G_BM, (Nmax + G_BN - 1) / G_BN, batch);
     size_t smem = zgemm_smem_bytes(amode, Kmax);
-    if (amode == A_NORMAL && !breal && p.accum && !p.triB && Kmax <= 64 && batch <= 65535 && !getenv("LLCK_NO_RANKK")) {
+    if (amode == A_NORMAL && !breal && p.accum && !p.triB && Kmax <= 64 && batch <= 65535) {
         if (Kmax <= 32) return bconjt ? zgemm_rankk_launch<32, true>(p, Nmax, batch, stream) : zgemm_rankk_launch<32, false>(p, Nmax, batch, stream);
         return bconjt ? zgemm_rankk_launch<64, true>(p, Nmax, batch, stream) : zgemm_rankk_launch<64, false>(p, Nmax, batch, stream);
     }
@@ -380,6 +380,7 @@ static inline cudaError_t zgemm_batched(int amode, const GemmParams& p, int Mmax
         if (e != cudaSuccess) return e;
         dim3 g32(1, (Nmax + GW_BN - 1) / GW_BN, batch);
         zgemm_w32_kernel<<<g32, 256, sm32, stream>>>(p);
+        LLCK_LAUNCHED();
         return cudaGetLastError();
     }
     if (amode == A_CONJT) return zgemm_launch<A_CONJT, false>(p, grid, smem, stream);

@@ -1,6 +1,6 @@
 // C-ABI of libllck.so: orchestration of the batched KBDM solve (see include/llck.h).
 // Pipeline per ensemble member (reference llckbdm/kbdm.py:19-92, 133-240):
-//   X <- Hankel(U^{p-1});  block-Jacobi SVD  X = L S, V = R                    (kbdm.py:166)
+//   X <- Hankel(U^{p-1}) = Q B P^H (blocked bidiagonalisation);  B = L_b S R_b^T by divide and conquer   (kbdm.py:166)
 //   Rs = R_l g^{-1/2},  Lt = L_l g^{-1/2}   (g = s or s + q^2/s)                (kbdm.py:171-186)
 //   T1 = U^p Rs (implicit Hankel GEMM);  Ured = Lt^H T1                         (kbdm.py:189)
 //   Ured = Q H Q^H -> Z T Z^H (Hessenberg + multishift QR);  Xev = trevc(T)     (kbdm.py:192)
@@ -10,7 +10,6 @@
 #include "../../include/llck.h"
 #include "common.cuh"
 #include "gemm.cuh"
-#include "svd.cuh"
 #include "eig.cuh"
 #include "bidiag.cuh"
 #include "svd_real.cuh"
@@ -19,6 +18,7 @@
 #include "silhouette.cuh"
 #include "features.cuh"
 #include "hdbscan_mst.cuh"
+#include "hdbscan_tree.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -65,16 +65,21 @@ __global__ void mark_unconverged_kernel(const int* done, int* status, int batch)
 }
 
 // members flagged by the divide-and-conquer SVD are the only ones the Jacobi path still has to solve
-__global__ void bdc_fallback_count_kernel(const int* fallback, int* done, int* count, int batch) {
+__global__ void fallback_to_done_kernel(const int* fallback, int* done, int batch) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) done[b] = fallback[b] ? 0 : 1;
+}
+
+// per-call device state: convergence flags, outputs that are accumulated with atomics
+__global__ void meta_zero_kernel(int* done, unsigned long long* sweep_off, int* status, int* n_valid, int* hqr_sweeps, int batch) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
-    done[b] = fallback[b] ? 0 : 1;
-    if (fallback[b]) atomicAdd(count, 1);
+    done[b] = 0; sweep_off[b] = 0ull; status[b] = 0; n_valid[b] = 0; hqr_sweeps[b] = 0;
 }
 
 // ---- workspace layout -----------------------------------------------------------------------------
 struct WsLayout {
-    size_t mv, lv, nbv, done, n_active, hqr_sweeps, perm, sig_off, sweep_off, tau, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, bdcvec, fallback, ypart, mats, total;
+    size_t mv, lv, nbv, done, hqr_sweeps, perm, sig_off, sweep_off, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, bdcvec, fallback, ypart, mats, total;
     int nmats;
 };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -85,12 +90,10 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
     L.lv = o; o = al256(o + sizeof(int) * batch);
     L.nbv = o; o = al256(o + sizeof(int) * batch);
     L.done = o; o = al256(o + sizeof(int) * batch);
-    L.n_active = o; o = al256(o + 256);
     L.hqr_sweeps = o; o = al256(o + sizeof(int) * batch);
     L.perm = o; o = al256(o + sizeof(int) * (size_t)batch * ld);
     L.sig_off = o; o = al256(o + sizeof(long long) * batch);
     L.sweep_off = o; o = al256(o + sizeof(unsigned long long) * batch);
-    L.tau = o; o = al256(o + sizeof(cplx) * (size_t)batch * ld);
     const size_t pan = sizeof(cplx) * (size_t)batch * ld * HB_NB;
     L.vp = o; o = al256(o + pan);
     L.yp = o; o = al256(o + pan);
@@ -127,13 +130,13 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
 // ---- thread-block cluster launches for small batches ----------------------------------------------------------------
 // largest power-of-two cluster size (<= 16) such that all `batch` clusters of `kernel` are co-resident in one wave
 template <typename K>
-static int pick_cluster_size(K kernel, int batch, int threads, size_t smem, int max_size) {
+static int pick_cluster_size(K kernel, int batch, int threads, size_t smem, int max_size, int forced) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess) return 1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
     int csize = 1;
     while (csize < max_size && 2 * csize * batch <= sms) csize *= 2;
-    if (const char* ev = getenv("LLCK_CLUSTER")) { int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) csize = v < max_size ? v : max_size; }
+    if (forced > 0) csize = forced < max_size ? forced : max_size;      // llck_options.cluster_size
     if (csize > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { (void)cudaGetLastError(); csize = 8; }
     while (csize > 1) {
         cudaLaunchConfig_t cfg = {};
@@ -154,6 +157,7 @@ static int pick_cluster_size(K kernel, int batch, int threads, size_t smem, int 
 
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_clustered(void (*kernel)(KArgs...), int batch, int csize, int threads, size_t smem, cudaStream_t st, Args... args) {
+    LLCK_LAUNCHED();
     if (csize <= 1) {
         kernel<<<batch, threads, smem, st>>>(args...);
         return cudaGetLastError();
@@ -173,14 +177,14 @@ static cudaError_t launch_clustered(void (*kernel)(KArgs...), int batch, int csi
 // TQws/TPws ((ld/32) x 32 x 32 each), dws/ews (ld doubles each) -- all per member with the given strides.
 static int bidiag_driver(cplx* A, cplx* Q, cplx* P, long long stride, int ld, const int* d_mv, int mmax, int batch,
                          cplx* VX, cplx* YU, cplx* Wp, long long pstride, cplx* TQws, cplx* TPws,
-                         double* dws, double* ews, cudaStream_t st, cplx* ypart = nullptr) {
+                         double* dws, double* ews, cudaStream_t st, cplx* ypart = nullptr, int forced_cluster = 0) {
     // VX = per member [V | X] (ld x 64), YU = per member [Y | U] (ld x 64): the panel's trailing update
     //   A[e:, e:] -= V Y^H + X U^H  is ONE rank-64 GEMM  A[e:, e:] -= [V X] [Y U]^H
     const long long pstride2 = 2 * pstride;
     cplx* Vp = VX; cplx* Xp = VX + pstride; cplx* Yp = YU; cplx* Up = YU + pstride;
     size_t sm = (size_t)(2 * ld + 2 * BD_NB * BD_NB + 8 * BD_NB + 8) * 16 + 512;
     CK(cudaFuncSetAttribute(bidiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const int bp_csize = (ypart != nullptr && batch <= 74) ? pick_cluster_size(bidiag_panel_kernel, batch, E_THREADS, sm, LLCK_MAX_CLUSTER) : 1;
+    const int bp_csize = (ypart != nullptr && batch <= 74) ? pick_cluster_size(bidiag_panel_kernel, batch, E_THREADS, sm, LLCK_MAX_CLUSTER, forced_cluster) : 1;
     int k0_last = 0;
     for (int k0 = 0; k0 < mmax; k0 += BD_NB) {
         k0_last = k0;
@@ -198,6 +202,7 @@ static int bidiag_driver(cplx* A, cplx* Q, cplx* P, long long stride, int ld, co
     dim3 gi(128, batch);
     set_identity_kernel<<<gi, 256, 0, st>>>(Q, stride, ld, d_mv);
     set_identity_kernel<<<gi, 256, 0, st>>>(P, stride, ld, d_mv);
+    llck_launch_count += 2;
     CK(cudaGetLastError());
     for (int right = 0; right < 2; ++right) {
         cplx* Acc = right ? P : Q;
@@ -206,6 +211,7 @@ static int bidiag_driver(cplx* A, cplx* Q, cplx* P, long long stride, int ld, co
             const int o = k0 + right;
             if (o >= mmax) continue;
             bidiag_qpanel_kernel<<<batch, E_THREADS, 0, st>>>(A, stride, ld, d_mv, k0, right, Vp, Yp /*VTh*/, pstride2, Tws, pstride);
+            LLCK_LAUNCHED();
             CK(cudaGetLastError());
             GemmParams g = gemm_params_zero();          // W = (V T^H)[o:, :]^H * Acc[o:, o:]
             g.A = Yp + o; g.strideA = pstride2; g.lda = ld;
@@ -292,11 +298,16 @@ int llck_bidiag_test(void* A, int32_t m, int32_t ld, double* d_out, double* e_ou
 int llck_rmse_batched(const void* data, int32_t N, double dwell, const double* line_lists, int64_t ll_stride,
                       const int32_t* n_rows, int32_t batch, int32_t filter, double amplitude_tol, double* rmse_out, void* stream) {
     if (!data || !line_lists || !n_rows || !rmse_out || N < 1 || batch < 1 || !(dwell > 0.0) || ll_stride < 4) return LLCK_E_BADARG;
-    const size_t sm = sizeof(cplx) * (size_t)N;
-    if (sm > 200 * 1024) return LLCK_E_BADARG;            // model FID is staged in shared memory (N <= 12800)
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaFuncSetAttribute(rmse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    rmse_kernel<<<batch, RMSE_THREADS, sm, st>>>((const cplx*)data, N, dwell, line_lists, ll_stride, n_rows, filter, amplitude_tol, rmse_out);
+    if (N <= RMSE_SMEM_POINTS) {                          // whole model FID staged in shared memory
+        const size_t sm = sizeof(cplx) * (size_t)N;
+        CK(cudaFuncSetAttribute(rmse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        rmse_kernel<<<batch, RMSE_THREADS, sm, st>>>((const cplx*)data, N, dwell, line_lists, ll_stride, n_rows, filter, amplitude_tol, rmse_out);
+    } else {                                              // long FIDs: tiled over n
+        const size_t sm = sizeof(cplx) * 2 * RMSE_TILE;
+        CK(cudaFuncSetAttribute(rmse_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        rmse_tiled_kernel<<<batch, RMSE_THREADS, sm, st>>>((const cplx*)data, N, dwell, line_lists, ll_stride, n_rows, filter, amplitude_tol, rmse_out);
+    }
     CK(cudaGetLastError());
     return 0;
 }
@@ -333,6 +344,22 @@ int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32
     hdb_prim_kernel<<<nfits, HDB_PRIM_THREADS, 0, (cudaStream_t)stream>>>(X, n, core, core_row, min_reach, cur_src,
                                                                           (long long*)mst_src, (long long*)mst_dst, mst_w);
     CK(cudaGetLastError());
+    return 0;
+}
+
+int llck_hdbscan_labels(const int64_t* mst_src, const int64_t* mst_dst, const double* mst_w, const int64_t* order, int32_t n, int32_t nfits,
+                        int32_t min_cluster_size, int32_t nthreads, int32_t* labels) {
+    if (!mst_src || !mst_dst || !mst_w || !labels || n < 1 || nfits < 1 || min_cluster_size < 2) return LLCK_E_BADARG;
+    const int64_t ne = (int64_t)n - 1;
+    for (int64_t i = 0; i < (int64_t)nfits * ne; ++i) {
+        if (mst_src[i] < 0 || mst_src[i] >= n || mst_dst[i] < 0 || mst_dst[i] >= n) return LLCK_E_BADARG;
+        if (order && (order[i] < 0 || order[i] >= ne)) return LLCK_E_BADARG;
+    }
+    try {
+        llck_hdb::labels_all_fits(mst_src, mst_dst, mst_w, order, n, nfits, min_cluster_size, nthreads, labels);
+    } catch (...) {
+        return LLCK_E_BADARG;
+    }
     return 0;
 }
 
@@ -379,99 +406,103 @@ int llck_bdc_test(const double* d, const double* e, const int32_t* m, int32_t ba
     return e3 == cudaSuccess ? 0 : -(int)e3;
 }
 
-int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int32_t* m, const int32_t* l,
+int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int64_t* sig_len, const int32_t* m, const int32_t* l,
                       int32_t p, double q, double dwell, int32_t batch,
                       double* line_lists, int64_t ll_stride,
                       void* mu_out, void* d_out, int64_t mu_stride,
                       double* sing_vals, int64_t sv_stride,
                       int32_t* n_valid, int32_t* status,
-                      void* workspace, size_t workspace_bytes, int32_t flags,
+                      void* workspace, size_t workspace_bytes, int32_t flags, const llck_options* opts,
                       void* stream, int32_t* info) {
-    if (!signals || !sig_offset || !m || !l || !line_lists || !sing_vals || !n_valid || !status || !workspace) return LLCK_E_BADARG;
-    if (batch <= 0 || p < 1 || q < 0.0) return LLCK_E_BADARG;
+    if (!signals || !sig_offset || !sig_len || !m || !l || !line_lists || !sing_vals || !n_valid || !status || !workspace) return LLCK_E_BADARG;
+    if (batch <= 0 || p < 1 || q < 0.0 || !(dwell > 0.0)) return LLCK_E_BADARG;
+    llck_options o;
+    memset(&o, 0, sizeof(o));
+    if (opts) {
+        if (opts->struct_size < (int32_t)sizeof(int32_t) || opts->struct_size > (int32_t)sizeof(llck_options)) return LLCK_E_BADARG;
+        memcpy(&o, opts, (size_t)opts->struct_size);
+    }
+    if (o.svd_mode != LLCK_SVD_DC && o.svd_mode != LLCK_SVD_JACOBI) return LLCK_E_BADARG;
+    if (o.cluster_size != 0 && o.cluster_size != 1 && o.cluster_size != 2 && o.cluster_size != 4 && o.cluster_size != 8) return LLCK_E_BADARG;
+    if (o.aed_window != 0 && (o.aed_window < 8 || o.aed_window > 48)) return LLCK_E_BADARG;
+    if (o.aed_nibble < 0 || o.aed_nibble > 1000 || o.jacobi_max_sweeps < 0 || o.jacobi_max_sweeps > 60) return LLCK_E_BADARG;
     int mmax = 0, lmax = 0;
     for (int b = 0; b < batch; ++b) {
         if (m[b] < 1 || l[b] < 1 || l[b] > m[b]) return LLCK_E_BADARG;
+        if (sig_offset[b] < 0 || sig_len[b] < 2 * (int64_t)m[b] + p - 1) return LLCK_E_SHORT_SIGNAL;    // kbdm.py:59-62: 2m + p - 1 <= N
         if (m[b] > mmax) mmax = m[b];
         if (l[b] > lmax) lmax = l[b];
         if (ll_stride < 4 * (int64_t)l[b] || sv_stride < m[b]) return LLCK_E_BADARG;
         if ((mu_out || d_out) && mu_stride < l[b]) return LLCK_E_BADARG;
     }
     const int ld = llck_leading_dim(mmax);
-    if (ld > 2048) return LLCK_E_BADARG;
+    if (ld > LLCK_M_MAX) return LLCK_E_TOO_LARGE;
     const WsLayout L = ws_layout(batch, ld, flags);
     if (workspace_bytes < L.total) return LLCK_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const bool timing = (flags & LLCK_FLAG_TIMING) != 0 && info != nullptr;
-    cudaEvent_t tev[10];
+    // CUDA events of the timing mode and the staged host metadata are released on every exit path
+    struct Guard {
+        cudaEvent_t tev[10]; int ntev_created = 0; void* host = nullptr;
+        ~Guard() { for (int i = 0; i < ntev_created; ++i) cudaEventDestroy(tev[i]); free(host); }
+    } G;
     int ntev = 0;
-    if (timing) for (int i = 0; i < 10; ++i) CK(cudaEventCreate(&tev[i]));
-#define TICK() do { if (timing) { CK(cudaEventRecord(tev[ntev++], st)); } } while (0)
+    if (timing) for (int i = 0; i < 10; ++i) { CK(cudaEventCreate(&G.tev[i])); G.ntev_created = i + 1; }
+#define TICK() do { if (timing) { CK(cudaEventRecord(G.tev[ntev++], st)); } } while (0)
     unsigned char* ws = (unsigned char*)workspace;
     int* d_mv = (int*)(ws + L.mv);
     int* d_lv = (int*)(ws + L.lv);
     int* d_nbv = (int*)(ws + L.nbv);
     int* d_done = (int*)(ws + L.done);
-    int* d_nact = (int*)(ws + L.n_active);
     int* d_hqrs = (int*)(ws + L.hqr_sweeps);
     int* d_perm = (int*)(ws + L.perm);
     long long* d_soff = (long long*)(ws + L.sig_off);
     unsigned long long* d_swoff = (unsigned long long*)(ws + L.sweep_off);
-    cplx* d_tau = (cplx*)(ws + L.tau);
     cplx* mats = (cplx*)(ws + L.mats);
     const long long stride = (long long)ld * ld;
     const bool dbg = (flags & LLCK_FLAG_DEBUG_KEEP) != 0;
     auto mat = [&](int i) { return mats + (size_t)i * batch * stride; };
     // buffer assignment (production aliases dead buffers; debug keeps all 14)
-    cplx *bX, *bV, *bRs, *bLt, *bT1, *bH, *bZ, *bXev, *bP, *bB, *bW;
-    if (dbg) { bX = mat(0); bV = mat(1); bRs = mat(2); bLt = mat(3); bT1 = mat(4); bH = mat(8); bZ = mat(9); bXev = mat(10); bP = mat(11); bB = mat(12); bW = mat(13); }
-    else     { bX = mat(0); bV = mat(1); bRs = mat(2); bLt = mat(3); bT1 = mat(0); bH = mat(1); bZ = mat(3); bXev = mat(0); bP = mat(4); bB = mat(5); bW = mat(0); }
+    cplx *bX, *bRs, *bLt, *bT1, *bH, *bZ, *bXev, *bP, *bB, *bW;
+    if (dbg) { bX = mat(0); bRs = mat(2); bLt = mat(3); bT1 = mat(4); bH = mat(8); bZ = mat(9); bXev = mat(10); bP = mat(11); bB = mat(12); bW = mat(13); }
+    else     { bX = mat(0); bRs = mat(2); bLt = mat(3); bT1 = mat(0); bH = mat(1); bZ = mat(3); bXev = mat(0); bP = mat(4); bB = mat(5); bW = mat(0); }
+    llck_launch_count = 0;
 
-    // ---- metadata ----
-    int* h_nb = (int*)malloc(sizeof(int) * batch);
-    if (!h_nb) return LLCK_E_BADARG;
+    // ---- metadata: per-member sizes and FID offsets go to the device through ONE staged copy; the call never waits for the stream ----
     int nbmax = 2;
-    for (int b = 0; b < batch; ++b) {
-        int nb = (m[b] + J_B - 1) / J_B;
-        if (nb < 2) nb = 2;
-        if (nb & 1) ++nb;
-        h_nb[b] = nb;
-        if (nb > nbmax) nbmax = nb;
+    {
+        const size_t meta_bytes = L.sig_off + sizeof(long long) * (size_t)batch - L.mv;     // mv | lv | nbv | done | ... | sig_off are contiguous
+        (void)meta_bytes;
+        int* h = (int*)malloc(sizeof(int) * (size_t)batch);
+        if (!h) return LLCK_E_BADARG;
+        G.host = h;
+        for (int b = 0; b < batch; ++b) {
+            int nb = (m[b] + J_B - 1) / J_B;
+            if (nb < 2) nb = 2;
+            if (nb & 1) ++nb;
+            h[b] = nb;
+            if (nb > nbmax) nbmax = nb;
+        }
+        // pageable -> device cudaMemcpyAsync returns once the source has been staged: the host arrays may be reused right after the call
+        CK(cudaMemcpyAsync(d_mv, m, sizeof(int) * batch, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_lv, l, sizeof(int) * batch, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_nbv, h, sizeof(int) * batch, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_soff, sig_offset, sizeof(long long) * batch, cudaMemcpyHostToDevice, st));
     }
-    cudaError_t e;
-    e = cudaMemcpyAsync(d_mv, m, sizeof(int) * batch, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_lv, l, sizeof(int) * batch, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_nbv, h_nb, sizeof(int) * batch, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_soff, sig_offset, sizeof(long long) * batch, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    free(h_nb);
-    if (e != cudaSuccess) return -(int)e;
-    CK(cudaMemsetAsync(d_done, 0, sizeof(int) * batch, st));
-    CK(cudaMemsetAsync(d_swoff, 0, sizeof(unsigned long long) * batch, st));
-    CK(cudaMemsetAsync(status, 0, sizeof(int) * batch, st));
-    CK(cudaMemsetAsync(n_valid, 0, sizeof(int) * batch, st));
-    CK(cudaMemsetAsync(d_hqrs, 0, sizeof(int) * batch, st));
+    meta_zero_kernel<<<(batch + 255) / 256, 256, 0, st>>>(d_done, d_swoff, status, n_valid, d_hqrs, batch);
+    LLCK_LAUNCHED();
+    CK(cudaGetLastError());
 
-    // ---- SVD of U^{p-1} ----
-    const char* smode = getenv("LLCK_SVD");
-    const bool svd_bidiag = !(smode && smode[0] == 'j');      // default: bidiagonalise + real Jacobi; LLCK_SVD=j: complex Jacobi on U directly
-    int sweeps_run = 0;
-    int launches = 1;   // svd_init
-    int jac_rounds = 0;
-    double upd_us = 0.0; int upd_launches = 0;
-    const bool verbose = getenv("LLCK_VERBOSE") != nullptr;
-    double conv2 = 1e-12;   // a member is converged when no pair exceeded 1e-6 (scaled) during a sweep: the sweep leaves <= ~1e-12
-    if (const char* ev = getenv("LLCK_JACOBI_CONV")) { double c = atof(ev); conv2 = c * c; }
-    int inner_sweeps = 1;
-    if (const char* ev = getenv("LLCK_JACOBI_INNER")) inner_sweeps = atoi(ev);
+    // ---- SVD of U^{p-1}: bidiagonalisation, then divide and conquer on the real bidiagonal ----
     TICK();   // 0
     {
         dim3 grid(256, batch);
-        svd_init_kernel<<<grid, 256, 0, st>>>(bX, bV, stride, ld, d_mv, d_nbv, (const cplx*)signals, d_soff, p - 1);
+        hankel_init_kernel<<<grid, 256, 0, st>>>(bX, stride, ld, d_mv, d_nbv, (const cplx*)signals, d_soff, p - 1);
+        LLCK_LAUNCHED();
         CK(cudaGetLastError());
     }
-    if (!svd_bidiag) TICK();   // 1: init done
-    if (svd_bidiag) {
+    const int max_sweeps = o.jacobi_max_sweeps > 0 ? o.jacobi_max_sweeps : 30;
+    {
         // (1) U^{p-1} = Q B P^H, B real upper bidiagonal
         cplx* bQ = dbg ? mat(9) : mat(1);
         cplx* bPm = dbg ? mat(11) : mat(4);
@@ -484,15 +515,15 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             // [V|X] lives in the (vp, yp) pair of panel buffers, [Y|U] in (vtp, wp): both pairs are contiguous in the workspace
             int rc = bidiag_driver(bX, bQ, bPm, stride, ld, d_mv, mmax, batch, (cplx*)(ws + L.vp), (cplx*)(ws + L.vtp),
                                    (cplx*)(ws + L.pan6), pstride, (cplx*)(ws + L.tws), (cplx*)(ws + L.pan7), dws, ews, st,
-                                   (cplx*)(ws + L.ypart));
+                                   (cplx*)(ws + L.ypart), o.cluster_size);
             if (rc) return rc;
         }
         TICK();   // 1: init + bidiagonalisation done
-        // (2) SVD of the real bidiagonal B: divide and conquer (default); members it flags as numerically rank deficient
-        //     (and every member with LLCK_SVD=b) go through the real block one-sided Jacobi
-        const bool use_dc = !(smode && smode[0] == 'b');
+        // (2) SVD of the real bidiagonal B: divide and conquer.  Members it flags as numerically rank deficient (and every member
+        //     with LLCK_SVD_JACOBI) are solved by the real block one-sided Jacobi.  The decision stays on the device: the Jacobi
+        //     rounds are always enqueued and their CTAs exit at once for members that are done (no host read-back).
+        const bool use_dc = (o.svd_mode == LLCK_SVD_DC);
         int* d_fallback = (int*)(ws + L.fallback);
-        int n_fallback = batch;
         BdcParams bp;
         if (use_dc) {
             const int nb0 = dbg ? 14 : 6;
@@ -504,28 +535,22 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             int rc = bdc_driver(bp, mmax, st);
             if (rc) return rc;
             bdc_sv_kernel<<<batch, 256, 0, st>>>(bp, sing_vals, sv_stride, d_fallback);
+            LLCK_LAUNCHED();
             dim3 grid(lmax, batch);
             bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_lv, sing_vals, sv_stride, q, bLpre, bRpre, stride, ld, status, d_fallback, 0);
+            LLCK_LAUNCHED();
+            fallback_to_done_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_fallback, d_done, batch);
+            LLCK_LAUNCHED();
             CK(cudaGetLastError());
-            CK(cudaMemsetAsync(d_nact, 0, sizeof(int), st));
-            bdc_fallback_count_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_fallback, d_done, d_nact, batch);
-            CK(cudaMemcpyAsync(&n_fallback, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            {
-                int lvmax = 0;
-                while ((1 << lvmax) < bdc_nleaf(mmax)) ++lvmax;
-                launches += 2 + 7 * lvmax + 3;     // init, leaves, 7 kernels per merge level, singular values, gather, fallback count
-            }
-            if (verbose) fprintf(stderr, "[llck] bidiagonal D&C: %d of %d members fall back to the Jacobi SVD\n", n_fallback, batch);
         }
         const int* d_only = use_dc ? d_fallback : nullptr;
         double* Xr = (double*)bReal;
         double* Vr = Xr + (long long)ld * ld;
         const long long rstride = 2 * stride;       // doubles per member
-        if (n_fallback > 0) {
         {
             dim3 grid(256, batch);
-            rsvd_init_kernel<<<grid, 256, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_nbv, dws, ews);
+            rsvd_init_kernel<<<grid, 256, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_nbv, dws, ews, d_only);
+            LLCK_LAUNCHED();
             CK(cudaGetLastError());
         }
         CK(cudaFuncSetAttribute(rjacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_GRAM_SMEM));
@@ -533,62 +558,36 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         CK(cudaFuncSetAttribute(rjacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_UPD_SMEM));
         RJacobiParams rp;
         rp.X = Xr; rp.V = Vr; rp.stride = rstride; rp.ld = ld; rp.mv = d_mv; rp.nbv = d_nbv; rp.sweep_off = d_swoff; rp.done = d_done;
-        rp.tol2 = 1e-28; rp.inner_sweeps = inner_sweeps;
+        rp.tol2 = 1e-28; rp.inner_sweeps = 1;
         rp.Jws = (double*)(ws + L.jws); rp.Gws = (double*)(ws + L.gws); rp.offws = (double*)(ws + L.offws); rp.skip = (int*)(ws + L.skip);
         rp.pairs_max = ((ld / J_B) + 1) / 2 + 1;
-        cudaEvent_t uev[128];
-        if (timing) for (int i = 0; i < 128; ++i) CK(cudaEventCreate(&uev[i]));
-        int h_active = n_fallback;
-        for (int sweep = 0; sweep < 30 && h_active > 0; ++sweep) {
+        // a member is converged when no pair exceeded 1e-6 (scaled) during a sweep: that sweep leaves <= ~1e-12
+        const double conv = o.jacobi_conv > 0.0 ? o.jacobi_conv : 1e-6;
+        for (int sweep = 0; sweep < max_sweeps; ++sweep) {
             for (int r = 0; r < nbmax - 1; ++r) {
                 rp.round = r;
                 dim3 gA(nbmax / 2, batch), gA2(nbmax / 2, batch, 2);
                 rjacobi_gram_kernel<<<gA, 256, RJ_GRAM_SMEM, st>>>(rp);
                 rjacobi_eig_kernel<<<gA, RJE_THREADS, RJE_SMEM, st>>>(rp);
-                if (timing && r < 64) CK(cudaEventRecord(uev[2 * r], st));
                 rjacobi_update_kernel<<<gA2, 256, RJ_UPD_SMEM, st>>>(rp);
-                if (timing && r < 64) CK(cudaEventRecord(uev[2 * r + 1], st));
+                llck_launch_count += 3;
             }
-            launches += 3 * (nbmax - 1) + 1;
-            CK(cudaGetLastError());
-            if (verbose) {
-                unsigned long long* h = (unsigned long long*)malloc(sizeof(unsigned long long) * batch);
-                CK(cudaMemcpyAsync(h, d_swoff, sizeof(unsigned long long) * batch, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                double mx = 0.0, mn = 1e300;
-                for (int b = 0; b < batch; ++b) { double v; memcpy(&v, &h[b], 8); v = sqrt(v); if (v > mx) mx = v; if (v < mn) mn = v; }
-                fprintf(stderr, "[llck] real jacobi sweep %d: active=%d  max off (pre-rotation) over members: max=%.3e min=%.3e\n", sweep, h_active, mx, mn);
-                free(h);
-            }
-            CK(cudaMemsetAsync(d_nact, 0, sizeof(int), st));
-            jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, d_nact, batch, conv2);
-            CK(cudaMemcpyAsync(&h_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            ++sweeps_run;
-            jac_rounds += nbmax - 1;
-            if (timing) {
-                for (int r = 0; r < nbmax - 1 && r < 64; ++r) {
-                    float ms = 0.f;
-                    CK(cudaEventElapsedTime(&ms, uev[2 * r], uev[2 * r + 1]));
-                    upd_us += 1000.0 * ms; ++upd_launches;
-                }
-            }
-        }
-        if (timing) for (int i = 0; i < 128; ++i) cudaEventDestroy(uev[i]);
-        if (h_active > 0) {
-            mark_unconverged_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_done, status, batch);
+            jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, batch, conv * conv);
+            LLCK_LAUNCHED();
             CK(cudaGetLastError());
         }
+        mark_unconverged_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_done, status, batch);
+        LLCK_LAUNCHED();
         // singular values, truncation/scaling of the Jacobi members
         int npow2 = 64;
         while (npow2 < ld) npow2 <<= 1;
         rsvd_finalize_kernel<<<batch, 256, npow2 * 12, st>>>(Xr, rstride, ld, d_mv, d_nbv, sing_vals, sv_stride, d_perm, npow2, d_only);
-        CK(cudaGetLastError());
+        LLCK_LAUNCHED();
         {
             dim3 grid(lmax, batch);
             rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 0, d_only);
+            LLCK_LAUNCHED();
             CK(cudaGetLastError());
-        }
         }
         TICK();   // 2: SVD of the bidiagonal done
         // (3) back-multiplication by Q and P
@@ -602,7 +601,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             CK(cudaMemsetAsync(mat(0), 0, sizeof(cplx) * batch * stride, st));
             CK(cudaMemsetAsync(mat(1), 0, sizeof(cplx) * batch * stride, st));
             dim3 grid(mmax, batch);
-            if (n_fallback > 0) rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 1, d_only);
+            rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 1, d_only);
             if (use_dc) bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_lv, sing_vals, sv_stride, q, bLpre, bRpre, stride, ld, status, d_fallback, 1);
             CK(cudaGetLastError());
             g.A = bQ; g.B = bLpre; g.C = mat(0); g.Nv = d_mv;
@@ -610,141 +609,8 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             g.A = bPm; g.B = bRpre; g.C = mat(1);
             CK(zgemm_batched(A_NORMAL, g, mmax, mmax, mmax, batch, st));
         }
-    } else {
-    CK(cudaFuncSetAttribute(jacobi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, J_SMEM_BYTES));
-    JacobiParams jp;
-    jp.X = bX; jp.V = bV; jp.stride = stride; jp.ld = ld; jp.mv = d_mv; jp.nbv = d_nbv;
-    jp.sweep_off = d_swoff; jp.done = d_done; jp.tol2 = 1e-28;
-    jp.inner_sweeps = inner_sweeps;
-    const int max_sweeps = 30;
-    int h_active = batch;
-    const char* jmode = getenv("LLCK_JACOBI");
-    const bool fused = (jmode && jmode[0] == 'f');
-    JacobiSplitParams sp;
-    sp.X = bX; sp.V = bV; sp.stride = stride; sp.ld = ld; sp.mv = d_mv; sp.nbv = d_nbv; sp.sweep_off = d_swoff; sp.done = d_done;
-    sp.tol2 = jp.tol2; sp.inner_sweeps = jp.inner_sweeps;
-    sp.Jws = (cplx*)(ws + L.jws); sp.skip = (int*)(ws + L.skip); sp.pairs_max = ((ld / J_B) + 1) / 2 + 1;
-    if (!fused) {
-        CK(cudaFuncSetAttribute(jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JS_GRAM_SMEM));
-        CK(cudaFuncSetAttribute(jacobi_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JS_UPD_SMEM));
     }
-    cudaEvent_t uev[128];
-    if (timing) for (int i = 0; i < 128; ++i) CK(cudaEventCreate(&uev[i]));
-    cudaStream_t st2 = nullptr;
-    cudaEvent_t ev2 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
-    const bool three = !fused && !(jmode && jmode[0] == '2');     // default: gram / eig / update kernels
-    cplx* Gws = (cplx*)(ws + L.gws);
-    double* offws = (double*)(ws + L.offws);
-    if (three) CK(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JE_SMEM));
-    const int nhalf = (!fused && !three && batch >= 8 && getenv("LLCK_JACOBI_2STREAM")) ? 2 : 1;
-    const int bsplit = (nhalf == 2) ? batch / 2 : batch;
-    if (nhalf == 2) {
-        CK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev1, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&evA, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&evB, cudaEventDisableTiming));
-    }
-    for (int sweep = 0; sweep < max_sweeps && h_active > 0; ++sweep) {
-        if (nhalf == 2) {   // st2 must see everything issued on st so far (init / previous sweep bookkeeping)
-            CK(cudaEventRecord(ev1, st));
-            CK(cudaStreamWaitEvent(st2, ev1, 0));
-        }
-        for (int r = 0; r < nbmax - 1; ++r) {
-            if (fused) {
-                jp.round = r;
-                dim3 grid(nbmax / 2, batch);
-                jacobi_step_kernel<<<grid, 256, J_SMEM_BYTES, st>>>(jp);
-            } else {
-                // two half-batches on two streams: the smem-bound Gram/eigen-solve kernel of one half co-resides with the
-                // DMMA-bound update kernel of the other half (both fit 2 CTAs/SM)
-                // Staggered schedule (cross-stream events): gram(B,r) starts when gram(A,r) is done, gram(A,r+1) when
-                // gram(B,r) is done -> at any time one half is in its eigen-solve while the other is in its DMMA update.
-                auto half_params = [&](int h) {
-                    const int b0 = h ? bsplit : 0;
-                    JacobiSplitParams q = sp;
-                    q.round = r;
-                    q.X = sp.X + (long long)b0 * stride; q.V = sp.V + (long long)b0 * stride;
-                    q.mv = sp.mv + b0; q.nbv = sp.nbv + b0; q.sweep_off = sp.sweep_off + b0; q.done = sp.done + b0;
-                    q.Jws = sp.Jws + (long long)b0 * sp.pairs_max * 4096; q.skip = sp.skip + (long long)b0 * sp.pairs_max;
-                    return q;
-                };
-                const int bnA = bsplit, bnB = batch - bsplit;
-                JacobiSplitParams qa = half_params(0);
-                dim3 gA(nbmax / 2, bnA), gA2(nbmax / 2, bnA, 2);
-                if (three) {
-                    jacobi_gram3_kernel<<<gA, 256, 2 * JS_GTILE * 16, st>>>(qa, Gws, offws);
-                    jacobi_eig_kernel<<<gA, JE_THREADS, JE_SMEM, st>>>(qa, Gws, offws);
-                    if (timing && r < 64) CK(cudaEventRecord(uev[2 * r], st));
-                    jacobi_update_kernel<<<gA2, 256, JS_UPD_SMEM, st>>>(qa);
-                    if (timing && r < 64) CK(cudaEventRecord(uev[2 * r + 1], st));
-                } else {
-                    jacobi_gram_kernel<<<gA, 256, JS_GRAM_SMEM, st>>>(qa);
-                    if (nhalf == 2) {
-                        JacobiSplitParams qb = half_params(1);
-                        dim3 gB(nbmax / 2, bnB), gB2(nbmax / 2, bnB, 2);
-                        CK(cudaEventRecord(evA, st));
-                        CK(cudaStreamWaitEvent(st2, evA, 0));
-                        jacobi_gram_kernel<<<gB, 256, JS_GRAM_SMEM, st2>>>(qb);
-                        CK(cudaEventRecord(evB, st2));
-                        jacobi_update_kernel<<<gA2, 256, JS_UPD_SMEM, st>>>(qa);
-                        CK(cudaStreamWaitEvent(st, evB, 0));
-                        jacobi_update_kernel<<<gB2, 256, JS_UPD_SMEM, st2>>>(qb);
-                    } else {
-                        jacobi_update_kernel<<<gA2, 256, JS_UPD_SMEM, st>>>(qa);
-                    }
-                }
-            }
-        }
-        if (!fused && nhalf == 2) {
-            CK(cudaEventRecord(ev2, st2));
-            CK(cudaStreamWaitEvent(st, ev2, 0));
-        }
-        launches += fused ? (nbmax - 1 + 1) : ((three ? 3 : 2 * nhalf) * (nbmax - 1) + 1);
-        CK(cudaGetLastError());
-        if (verbose) {
-            unsigned long long* h = (unsigned long long*)malloc(sizeof(unsigned long long) * batch);
-            CK(cudaMemcpyAsync(h, d_swoff, sizeof(unsigned long long) * batch, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            double mx = 0.0, mn = 1e300;
-            for (int b = 0; b < batch; ++b) { double v; memcpy(&v, &h[b], 8); v = sqrt(v); if (v > mx) mx = v; if (v < mn) mn = v; }
-            fprintf(stderr, "[llck] jacobi sweep %d: active=%d  max off (pre-rotation) over members: max=%.3e min=%.3e\n", sweep, h_active, mx, mn);
-            free(h);
-        }
-        CK(cudaMemsetAsync(d_nact, 0, sizeof(int), st));
-        jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, d_nact, batch, conv2);
-        CK(cudaMemcpyAsync(&h_active, d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        ++sweeps_run;
-        jac_rounds += nbmax - 1;
-        if (timing && three) {
-            for (int r = 0; r < nbmax - 1 && r < 64; ++r) {
-                float ms = 0.f;
-                CK(cudaEventElapsedTime(&ms, uev[2 * r], uev[2 * r + 1]));
-                upd_us += 1000.0 * ms; ++upd_launches;
-            }
-        }
-    }
-    if (timing) for (int i = 0; i < 128; ++i) cudaEventDestroy(uev[i]);
-    if (nhalf == 2) {
-        cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(evA); cudaEventDestroy(evB); cudaStreamDestroy(st2);
-    }
-    TICK();   // 2: jacobi done
-    if (h_active > 0) {
-        mark_unconverged_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_done, status, batch);
-        CK(cudaGetLastError());
-    }
-    {
-        int npow2 = 64;
-        while (npow2 < ld) npow2 <<= 1;
-        svd_finalize_kernel<<<batch, 256, npow2 * 12, st>>>(bX, stride, ld, d_mv, d_nbv, sing_vals, sv_stride, d_perm, npow2);
-        CK(cudaGetLastError());
-        dim3 grid(lmax, batch);
-        svd_gather_kernel<<<grid, 128, 0, st>>>(bX, bV, stride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bRs, bLt, status);
-        CK(cudaGetLastError());
-    }
-    }
-    TICK();   // 3: finalize+gather done
+    TICK();   // 3: back-multiplication done
     // ---- reduced operator ----
     GemmParams gp = gemm_params_zero();
     gp.sig = (const cplx*)signals; gp.sig_off = d_soff;
@@ -765,97 +631,91 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
     TICK();   // 4: T1 + Ured done
     // ---- eigen-decomposition of Ured ----
     {
-        const char* hmode = getenv("LLCK_HESS");
-        if (hmode && hmode[0] == 'u') {
-            size_t sm = (size_t)ld * 16 + 512;
-            CK(cudaFuncSetAttribute(hessenberg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            hessenberg_kernel<<<batch, E_THREADS, sm, st>>>(bH, bZ, stride, ld, d_lv, d_tau);
+        // blocked (compact-WY) Hessenberg reduction: panel kernel + DMMA trailing updates
+        cplx* Vp = (cplx*)(ws + L.vp); cplx* Yp = (cplx*)(ws + L.yp); cplx* VTp = (cplx*)(ws + L.vtp);
+        cplx* Wp = (cplx*)(ws + L.wp); cplx* Tws = (cplx*)(ws + L.tws);
+        const long long pstride = (long long)ld * HB_NB;
+        size_t sm = (size_t)(2 * ld + HB_NB * HB_NB + 4 * HB_NB) * 16 + 512;
+        CK(cudaFuncSetAttribute(hess_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        const int hp_csize = (batch <= 74) ? pick_cluster_size(hess_panel_kernel, batch, E_THREADS, sm, LLCK_MAX_CLUSTER, o.cluster_size) : 1;
+        GemmParams hp = gemm_params_zero();
+        int k0_last = 0;
+        for (int k0 = 0; k0 + 2 < lmax; k0 += HB_NB) {
+            k0_last = k0;
+            CK(launch_clustered(hess_panel_kernel, batch, hp_csize, E_THREADS, sm, st, bH, stride, ld, d_lv, k0, Vp, Yp, VTp, pstride, Tws, pstride,
+                                (cplx*)(ws + L.ypart), hp_csize));
+            const int e = k0 + HB_NB;
+            const int r0 = k0 + 1;
+            // rows 0..k0 were left out of the panel kernel:  Y[0:r0, :] = A[0:r0, r0:] * (V T)[r0:, :]
+            hp = gemm_params_zero();
+            hp.A = bH + (long long)ld * r0; hp.strideA = stride; hp.lda = ld;
+            hp.B = VTp + r0; hp.strideB = pstride; hp.ldb = ld;
+            hp.C = Yp; hp.strideC = pstride; hp.ldc = ld;
+            hp.Mc = r0; hp.Nc = HB_NB; hp.Kv = d_lv; hp.Kc = -r0;
+            CK(zgemm_batched(A_NORMAL, hp, r0, HB_NB, lmax - r0, batch, st));
+            // ... and the panel's own columns above the panel:  A[0:r0, r0:e] -= Y[0:r0, :] * V[r0:e, :]^H
+            hp = gemm_params_zero();
+            hp.A = Yp; hp.strideA = pstride; hp.lda = ld;
+            hp.B = Vp + r0; hp.strideB = pstride; hp.ldb = ld;
+            hp.C = bH + (long long)ld * r0; hp.strideC = stride; hp.ldc = ld;
+            hp.Mc = r0; hp.Nc = HB_NB - 1; hp.Kc = HB_NB; hp.accum = 1;
+            CK(zgemm_batched(A_NORMAL, hp, r0, HB_NB - 1, HB_NB, batch, st, true));
+            if (e >= lmax) continue;
+            // A[:, e:] -= Y * V[e:, :]^H
+            hp = gemm_params_zero();
+            hp.A = Yp; hp.strideA = pstride; hp.lda = ld;
+            hp.B = Vp + e; hp.strideB = pstride; hp.ldb = ld;
+            hp.C = bH + (long long)ld * e; hp.strideC = stride; hp.ldc = ld;
+            hp.Mv = d_lv; hp.Nv = d_lv; hp.Nc = -e; hp.Kc = HB_NB; hp.accum = 1;
+            CK(zgemm_batched(A_NORMAL, hp, lmax, lmax - e, HB_NB, batch, st, true));
+            // W = (V T)[k0+1:, :]^H * A[k0+1:, e:]
+            hp = gemm_params_zero();
+            hp.A = VTp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
+            hp.B = bH + (k0 + 1) + (long long)ld * e; hp.strideB = stride; hp.ldb = ld;
+            hp.C = Wp; hp.strideC = pstride; hp.ldc = HB_NB;
+            hp.Mc = HB_NB; hp.Nv = d_lv; hp.Nc = -e; hp.Kv = d_lv; hp.Kc = -(k0 + 1);
+            CK(zgemm_batched(A_CONJT, hp, HB_NB, lmax - e, lmax - k0 - 1, batch, st));
+            // A[k0+1:, e:] -= V[k0+1:, :] * W
+            hp = gemm_params_zero();
+            hp.A = Vp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
+            hp.B = Wp; hp.strideB = pstride; hp.ldb = HB_NB;
+            hp.C = bH + (k0 + 1) + (long long)ld * e; hp.strideC = stride; hp.ldc = ld;
+            hp.Mv = d_lv; hp.Mc = -(k0 + 1); hp.Nv = d_lv; hp.Nc = -e; hp.Kc = HB_NB; hp.accum = 1;
+            CK(zgemm_batched(A_NORMAL, hp, lmax - k0 - 1, lmax - e, HB_NB, batch, st));
+        }
+        // Q = P_0 ... P_{n-3}: blocked backward accumulation
+        {
+            dim3 grid(128, batch);
+            set_identity_kernel<<<grid, 256, 0, st>>>(bZ, stride, ld, d_lv);
+            LLCK_LAUNCHED();
             CK(cudaGetLastError());
-        } else {
-            // blocked (compact-WY) reduction: panel kernel + DMMA trailing updates
-            cplx* Vp = (cplx*)(ws + L.vp); cplx* Yp = (cplx*)(ws + L.yp); cplx* VTp = (cplx*)(ws + L.vtp);
-            cplx* Wp = (cplx*)(ws + L.wp); cplx* Tws = (cplx*)(ws + L.tws);
-            const long long pstride = (long long)ld * HB_NB;
-            size_t sm = (size_t)(2 * ld + HB_NB * HB_NB + 4 * HB_NB) * 16 + 512;
-            CK(cudaFuncSetAttribute(hess_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            const int hp_csize = (batch <= 74) ? pick_cluster_size(hess_panel_kernel, batch, E_THREADS, sm, LLCK_MAX_CLUSTER) : 1;
-            if (verbose) fprintf(stderr, "[llck] hess_panel: %d CTA(s) per member\n", hp_csize);
-            GemmParams hp = gemm_params_zero();
-            int k0_last = 0;
-            for (int k0 = 0; k0 + 2 < lmax; k0 += HB_NB) {
-                k0_last = k0;
-                CK(launch_clustered(hess_panel_kernel, batch, hp_csize, E_THREADS, sm, st, bH, stride, ld, d_lv, k0, Vp, Yp, VTp, pstride, Tws, pstride,
-                                    (cplx*)(ws + L.ypart), hp_csize));
-                const int e = k0 + HB_NB;
-                const int r0 = k0 + 1;
-                // rows 0..k0 were left out of the panel kernel:  Y[0:r0, :] = A[0:r0, r0:] * (V T)[r0:, :]
-                hp = gemm_params_zero();
-                hp.A = bH + (long long)ld * r0; hp.strideA = stride; hp.lda = ld;
-                hp.B = VTp + r0; hp.strideB = pstride; hp.ldb = ld;
-                hp.C = Yp; hp.strideC = pstride; hp.ldc = ld;
-                hp.Mc = r0; hp.Nc = HB_NB; hp.Kv = d_lv; hp.Kc = -r0;
-                CK(zgemm_batched(A_NORMAL, hp, r0, HB_NB, lmax - r0, batch, st));
-                // ... and the panel's own columns above the panel:  A[0:r0, r0:e] -= Y[0:r0, :] * V[r0:e, :]^H
-                hp = gemm_params_zero();
-                hp.A = Yp; hp.strideA = pstride; hp.lda = ld;
-                hp.B = Vp + r0; hp.strideB = pstride; hp.ldb = ld;
-                hp.C = bH + (long long)ld * r0; hp.strideC = stride; hp.ldc = ld;
-                hp.Mc = r0; hp.Nc = HB_NB - 1; hp.Kc = HB_NB; hp.accum = 1;
-                CK(zgemm_batched(A_NORMAL, hp, r0, HB_NB - 1, HB_NB, batch, st, true));
-                if (e >= lmax) continue;
-                // A[:, e:] -= Y * V[e:, :]^H
-                hp = gemm_params_zero();
-                hp.A = Yp; hp.strideA = pstride; hp.lda = ld;
-                hp.B = Vp + e; hp.strideB = pstride; hp.ldb = ld;
-                hp.C = bH + (long long)ld * e; hp.strideC = stride; hp.ldc = ld;
-                hp.Mv = d_lv; hp.Nv = d_lv; hp.Nc = -e; hp.Kc = HB_NB; hp.accum = 1;
-                CK(zgemm_batched(A_NORMAL, hp, lmax, lmax - e, HB_NB, batch, st, true));
-                // W = (V T)[k0+1:, :]^H * A[k0+1:, e:]
+        }
+        if (lmax > 2) {
+            for (int k0 = k0_last; k0 >= 0; k0 -= HB_NB) {
+                hess_qpanel_kernel<<<batch, E_THREADS, 0, st>>>(bH, stride, ld, d_lv, k0, Vp, VTp, pstride, Tws, pstride);
+                LLCK_LAUNCHED();
+                CK(cudaGetLastError());
+                // W = (V T^H)[k0+1:, :]^H * Q[k0+1:, k0+1:]
                 hp = gemm_params_zero();
                 hp.A = VTp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
-                hp.B = bH + (k0 + 1) + (long long)ld * e; hp.strideB = stride; hp.ldb = ld;
+                hp.B = bZ + (k0 + 1) + (long long)ld * (k0 + 1); hp.strideB = stride; hp.ldb = ld;
                 hp.C = Wp; hp.strideC = pstride; hp.ldc = HB_NB;
-                hp.Mc = HB_NB; hp.Nv = d_lv; hp.Nc = -e; hp.Kv = d_lv; hp.Kc = -(k0 + 1);
-                CK(zgemm_batched(A_CONJT, hp, HB_NB, lmax - e, lmax - k0 - 1, batch, st));
-                // A[k0+1:, e:] -= V[k0+1:, :] * W
+                hp.Mc = HB_NB; hp.Nv = d_lv; hp.Nc = -(k0 + 1); hp.Kv = d_lv; hp.Kc = -(k0 + 1);
+                CK(zgemm_batched(A_CONJT, hp, HB_NB, lmax - k0 - 1, lmax - k0 - 1, batch, st));
+                // Q[k0+1:, k0+1:] -= V[k0+1:, :] * W
                 hp = gemm_params_zero();
                 hp.A = Vp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
                 hp.B = Wp; hp.strideB = pstride; hp.ldb = HB_NB;
-                hp.C = bH + (k0 + 1) + (long long)ld * e; hp.strideC = stride; hp.ldc = ld;
-                hp.Mv = d_lv; hp.Mc = -(k0 + 1); hp.Nv = d_lv; hp.Nc = -e; hp.Kc = HB_NB; hp.accum = 1;
-                CK(zgemm_batched(A_NORMAL, hp, lmax - k0 - 1, lmax - e, HB_NB, batch, st));
+                hp.C = bZ + (k0 + 1) + (long long)ld * (k0 + 1); hp.strideC = stride; hp.ldc = ld;
+                hp.Mv = d_lv; hp.Mc = -(k0 + 1); hp.Nv = d_lv; hp.Nc = -(k0 + 1); hp.Kc = HB_NB; hp.accum = 1;
+                CK(zgemm_batched(A_NORMAL, hp, lmax - k0 - 1, lmax - k0 - 1, HB_NB, batch, st));
             }
-            // Q = P_0 ... P_{n-3}: blocked backward accumulation
-            {
-                dim3 grid(128, batch);
-                set_identity_kernel<<<grid, 256, 0, st>>>(bZ, stride, ld, d_lv);
-                CK(cudaGetLastError());
-            }
-            if (lmax > 2) {
-                for (int k0 = k0_last; k0 >= 0; k0 -= HB_NB) {
-                    hess_qpanel_kernel<<<batch, E_THREADS, 0, st>>>(bH, stride, ld, d_lv, k0, Vp, VTp, pstride, Tws, pstride);
-                    CK(cudaGetLastError());
-                    // W = (V T^H)[k0+1:, :]^H * Q[k0+1:, k0+1:]
-                    hp = gemm_params_zero();
-                    hp.A = VTp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
-                    hp.B = bZ + (k0 + 1) + (long long)ld * (k0 + 1); hp.strideB = stride; hp.ldb = ld;
-                    hp.C = Wp; hp.strideC = pstride; hp.ldc = HB_NB;
-                    hp.Mc = HB_NB; hp.Nv = d_lv; hp.Nc = -(k0 + 1); hp.Kv = d_lv; hp.Kc = -(k0 + 1);
-                    CK(zgemm_batched(A_CONJT, hp, HB_NB, lmax - k0 - 1, lmax - k0 - 1, batch, st));
-                    // Q[k0+1:, k0+1:] -= V[k0+1:, :] * W
-                    hp = gemm_params_zero();
-                    hp.A = Vp + (k0 + 1); hp.strideA = pstride; hp.lda = ld;
-                    hp.B = Wp; hp.strideB = pstride; hp.ldb = HB_NB;
-                    hp.C = bZ + (k0 + 1) + (long long)ld * (k0 + 1); hp.strideC = stride; hp.ldc = ld;
-                    hp.Mv = d_lv; hp.Mc = -(k0 + 1); hp.Nv = d_lv; hp.Nc = -(k0 + 1); hp.Kc = HB_NB; hp.accum = 1;
-                    CK(zgemm_batched(A_NORMAL, hp, lmax - k0 - 1, lmax - k0 - 1, HB_NB, batch, st));
-                }
-            }
-            {
-                dim3 grid(128, batch);
-                clear_below_subdiag_kernel<<<grid, 256, 0, st>>>(bH, stride, ld, d_lv);
-                CK(cudaGetLastError());
-            }
+        }
+        {
+            dim3 grid(128, batch);
+            clear_below_subdiag_kernel<<<grid, 256, 0, st>>>(bH, stride, ld, d_lv);
+            LLCK_LAUNCHED();
+            CK(cudaGetLastError());
         }
         if (dbg) {
             CK(cudaMemcpyAsync(mat(6), bH, sizeof(cplx) * batch * stride, cudaMemcpyDeviceToDevice, st));
@@ -863,50 +723,22 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         }
         TICK();   // 5: hessenberg done
         CK(cudaFuncSetAttribute(hqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HQR_SMEM_BYTES));
-        long long* d_prof = nullptr;
-        if (verbose) { CK(cudaMalloc(&d_prof, sizeof(long long) * 10 * batch)); }
-        int hqr_trains = 1;
-        if (const char* ev = getenv("LLCK_HQR_TRAINS")) hqr_trains = atoi(ev) > 1 ? 2 : 1;
-        int aed_nw = E_NW, nibble = 0;      // 0: adaptive
-        if (const char* ev = getenv("LLCK_AED_NIBBLE")) { int v = atoi(ev); if (v >= 1 && v <= 1000) nibble = v; }
-        if (const char* ev = getenv("LLCK_AED_NW")) { int v = atoi(ev); if (v >= 8 && v <= 48) aed_nw = v; }
+        const int aed_nw = o.aed_window > 0 ? o.aed_window : E_NW;
         // small batches: a thread-block cluster of csize CTAs per member shares the strip GEMMs (the window chase / AED run redundantly in
         // every CTA of the cluster); csize = largest power of two that still gives every cluster its own SMs
-        const int csize = (batch <= 74) ? pick_cluster_size(hqr_kernel, batch, E_THREADS, HQR_SMEM_BYTES, LLCK_MAX_CLUSTER) : 1;
-        CK(launch_clustered(hqr_kernel, batch, csize, E_THREADS, HQR_SMEM_BYTES, st, bH, bZ, stride, ld, d_lv, status, d_hqrs, d_prof, hqr_trains, aed_nw, nibble, csize));
-        if (verbose) fprintf(stderr, "[llck] hqr: %d CTA(s) per member\n", csize);
-        if (verbose) {
-            long long* hp = (long long*)malloc(sizeof(long long) * 10 * batch);
-            CK(cudaMemcpyAsync(hp, d_prof, sizeof(long long) * 10 * batch, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            double tot[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int b = 0; b < batch; ++b) for (int i = 0; i < 10; ++i) tot[i] += (double)hp[10 * b + i] / batch;
-            fprintf(stderr, "[llck] hqr phase Mcycles/member: aed_schur=%.1f load=%.1f chase=%.1f store=%.1f strips=%.1f small=%.1f | AED: reorder=%.1f warp_total=%.1f strips=%.1f calls=%.0f\n",
-                    tot[0] / 1e6, tot[1] / 1e6, tot[2] / 1e6, tot[3] / 1e6, tot[4] / 1e6, tot[5] / 1e6, tot[6] / 1e6, tot[7] / 1e6, tot[8] / 1e6, tot[9]);
-            double mn = 1e300, mx = 0;
-            for (int b = 0; b < batch; ++b) {
-                double t = 0; for (int i = 0; i < 9; ++i) t += (double)hp[10 * b + i];
-                if (t < mn) mn = t;
-                if (t > mx) mx = t;
-            }
-            fprintf(stderr, "[llck] hqr per-member total Mcycles: min=%.1f max=%.1f\n", mn / 1e6, mx / 1e6);
-            free(hp); cudaFree(d_prof);
-
-        }
+        const int csize = (batch <= 74) ? pick_cluster_size(hqr_kernel, batch, E_THREADS, HQR_SMEM_BYTES, LLCK_MAX_CLUSTER, o.cluster_size) : 1;
+        CK(launch_clustered(hqr_kernel, batch, csize, E_THREADS, HQR_SMEM_BYTES, st, bH, bZ, stride, ld, d_lv, status, d_hqrs,
+                            (long long*)o.hqr_profile, 1, aed_nw, (int)o.aed_nibble, csize));
         TICK();   // 6: hqr done
-        const char* tmode = getenv("LLCK_TREVC");
-        if (tmode && tmode[0] == 'u') {
-            size_t sm2 = (size_t)ld * 32 + 512;
-            CK(cudaFuncSetAttribute(trevc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-            trevc_kernel<<<batch, E_THREADS, sm2, st>>>(bH, bXev, stride, ld, d_lv);
-            CK(cudaGetLastError());
-        } else {
+        {
             dim3 gz(128, batch);
             trevc_zero_kernel<<<gz, 256, 0, st>>>(bXev, stride, ld, d_lv);
+            LLCK_LAUNCHED();
             CK(cudaGetLastError());
             for (int j0 = ((lmax - 1) / TV_NB) * TV_NB; j0 >= 0; j0 -= TV_NB) {
                 dim3 gd((lmax - j0 + 127) / 128, batch);
                 trevc_diag_kernel<<<gd, 128, 0, st>>>(bH, bXev, stride, ld, d_lv, j0);
+                LLCK_LAUNCHED();
                 CK(cudaGetLastError());
                 if (j0 > 0) {
                     // X[0:j0, j0:n] -= T[0:j0, j0:j0+32] * X[j0:j0+32, j0:n]
@@ -920,6 +752,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
             }
             dim3 gn((lmax + 7) / 8, batch);
             trevc_normalize_kernel<<<gn, 256, 0, st>>>(bXev, stride, ld, d_lv);
+            LLCK_LAUNCHED();
             CK(cudaGetLastError());
         }
     }
@@ -945,46 +778,36 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int3
         dim3 grid((lmax + 7) / 8, batch);
         epilogue_kernel<<<grid, 256, 0, st>>>(bB, bW, bH, stride, ld, d_mv, d_lv, dwell, line_lists, ll_stride,
                                               (cplx*)mu_out, (cplx*)d_out, mu_stride, n_valid, status);
+        LLCK_LAUNCHED();
         CK(cudaGetLastError());
     }
     TICK();   // 9: epilogue done
-    int h_maxs = 0;
     if (info) {
-        // max QR sweeps over the batch (diagnostic)
-        int* h = (int*)malloc(sizeof(int) * batch);
+        for (int i = 0; i < 16; ++i) info[i] = 0;
+        info[2] = ld; info[3] = nbmax;
+        info[13] = llck_launch_count;                 // kernels enqueued by this call, counted at the launch sites
+        info[14] = max_sweeps * (nbmax - 1);          // Jacobi rounds enqueued (their CTAs exit at once for members the D&C solved)
+    }
+    if (timing) {
+        // diagnostic mode: the only path that waits for the stream.  info[1] = max QR sweeps over the batch,
+        // info[4..12] = stage durations in microseconds
+        int* h = (int*)malloc(sizeof(int) * (size_t)batch);
         if (h) {
             cudaError_t e3 = cudaMemcpyAsync(h, d_hqrs, sizeof(int) * batch, cudaMemcpyDeviceToHost, st);
             if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(st);
+            int h_maxs = 0;
             if (e3 == cudaSuccess) for (int b = 0; b < batch; ++b) if (h[b] > h_maxs) h_maxs = h[b];
             free(h);
             if (e3 != cudaSuccess) return -(int)e3;
+            info[1] = h_maxs;
+        } else {
+            CK(cudaStreamSynchronize(st));
         }
-        info[0] = sweeps_run; info[1] = h_maxs; info[2] = ld; info[3] = nbmax;
-        // kernel launches of this call (panel loops counted from their trip counts)
-        const int nbp = (mmax + BD_NB - 1) / BD_NB;                       // bidiagonalisation panels
-        const int nhp = lmax > 2 ? (lmax - 2 + HB_NB - 1) / HB_NB : 0;    // Hessenberg panels
-        const int ntb = (lmax - 1) / TV_NB + 1;                           // trevc blocks
-        int total = launches;
-        if (svd_bidiag) total += nbp + (nbp - 1) + 2 + 2 * nbp * 3 + 2;   // panels, trailing updates, Q/P accumulation, back-multiplication
-        else total += 2;                                                  // finalize, gather
-        total += 2;                                                       // T1, Ured
-        total += nhp + 3 * (nhp > 0 ? nhp - 1 : 0) + 1 + 3 * nhp + 1;     // Hessenberg panels + updates, identity, Q accumulation, clear
-        total += 1;                                                       // hqr
-        total += 1 + ntb + (ntb - 1) + 1;                                 // trevc
-        total += 3 + 1;                                                   // P, B, W, epilogue
-        info[13] = total;
-        info[14] = jac_rounds;   // Jacobi rounds (one gram + eig + update launch each)
-        info[15] = (upd_launches > 0) ? (int32_t)(upd_us / upd_launches) : 0;   // avg jacobi_update_kernel duration (us), timing mode
-    }
-    CK(cudaStreamSynchronize(st));
-    if (timing) {
-        // info[4..12]: stage durations in microseconds: init, jacobi, finalize+gather, T1+Ured, hessenberg, hqr, trevc, P+B+W, epilogue
         for (int i = 0; i + 1 < ntev; ++i) {
             float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, tev[i], tev[i + 1]));
+            CK(cudaEventElapsedTime(&ms, G.tev[i], G.tev[i + 1]));
             info[4 + i] = (int32_t)(ms * 1000.0f);
         }
-        for (int i = 0; i < 10; ++i) cudaEventDestroy(tev[i]);
     }
 #undef TICK
     return 0;

@@ -1,11 +1,50 @@
 // SVD of the REAL upper-bidiagonal B (from bidiag.cuh) by block one-sided Jacobi in real FP64 arithmetic -- second half
-// of the replacement of scipy.linalg.svd (reference llckbdm/kbdm.py:166).  Same scheme as svd.cuh (round-robin pairs of
-// 32-column blocks; Gram on DMMA -> two-sided Jacobi eigen-solve of the 64x64 Gram in shared memory -> DMMA update of
-// the X and V panels), but one real DMMA per 8x8x4 tile product instead of four, and half the bytes.
+// of the replacement of scipy.linalg.svd (reference llckbdm/kbdm.py:166), used for the members the divide-and-conquer
+// solver (bdc.cuh) flags as numerically rank deficient.  Round-robin pairs of
+// 32-column blocks: Gram on DMMA -> two-sided Jacobi eigen-solve of the 64x64 Gram in shared memory (relative-accuracy
+// preserving, Demmel-Veselic) -> DMMA update of the X and V panels; one real DMMA per 8x8x4 tile product.
 //   X <- B, V <- I;  on exit X = L_b Sigma, V = R_b  with  B = L_b Sigma R_b^T;  then U0 = (Q L_b) Sigma (P R_b)^H.
 #pragma once
 #include "common.cuh"
-#include "svd.cuh"
+
+#define J_B 32                            // columns per Jacobi block
+
+// ---- working copy of the Hankel matrix: X = U^{shift} (zero padded to ld x mp) -----------------------------------
+__global__ void hankel_init_kernel(cplx* X, long long stride, int ld, const int* mv, const int* nbv,
+                                   const cplx* sig, const long long* sig_off, int shift) {
+    const int b = blockIdx.y;
+    const int m = mv[b], mp = nbv[b] * J_B;
+    const cplx* c = sig + sig_off[b] + shift;
+    cplx* Xb = X + (long long)b * stride;
+    const long long total = (long long)ld * mp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(idx % ld), j = (int)(idx / ld);
+        Xb[idx] = (i < m && j < m) ? c[i + j] : mkc(0.0, 0.0);
+    }
+}
+
+// round-robin pairing of n (even) players, round r in [0, n-1), pair q in [0, n/2)
+__device__ __forceinline__ void rr_pair(int n, int r, int q, int& a, int& b) {
+    if (q == 0) { a = n - 1; b = r; }
+    else {
+        a = (r + q) % (n - 1);
+        b = (r - q + (n - 1)) % (n - 1);
+    }
+    if (a > b) { int t = a; a = b; b = t; }
+}
+
+__device__ __forceinline__ int pk(int r, int c) { return ((c * (c + 1)) >> 1) + r; }      // packed upper triangle, r <= c
+
+// ---- end of sweep: convergence bookkeeping (device side only; the host never reads it back) ----------------------
+__global__ void jacobi_sweep_end_kernel(unsigned long long* sweep_off, int* done, int batch, double conv2) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    if (!done[b]) {
+        double off2 = __longlong_as_double((long long)sweep_off[b]);
+        if (off2 < conv2) done[b] = 1;
+    }
+    sweep_off[b] = 0ull;
+}
 
 #define RJ_RC 64                          // rows per staged chunk
 #define RJ_LDT 68                         // tile ld in doubles (= 4 mod 16: conflict-free LDS.64 fragment reads)
@@ -32,8 +71,9 @@ struct RJacobiParams {
 };
 
 __global__ void rsvd_init_kernel(double* X, double* V, long long stride, int ld, const int* mv, const int* nbv,
-                                 const double* dws, const double* ews) {
+                                 const double* dws, const double* ews, const int* only) {
     const int b = blockIdx.y;
+    if (only && !only[b]) return;          // member already solved by the divide-and-conquer path
     const int m = mv[b], mp = nbv[b] * J_B;
     double* Xb = X + (long long)b * stride;
     double* Vb = V + (long long)b * stride;
@@ -350,7 +390,7 @@ __global__ void __launch_bounds__(256, 2) rjacobi_update_kernel(RJacobiParams p)
     }
 }
 
-// column norms of X -> singular values sorted descending + permutation (real twin of svd_finalize_kernel)
+// column norms of X -> singular values sorted descending + permutation 
 __global__ void __launch_bounds__(256) rsvd_finalize_kernel(const double* X, long long stride, int ld, const int* mv, const int* nbv,
                                                             double* sing_vals, long long sv_stride, int* perm_out, int npow2,
                                                             const int* only = nullptr) {

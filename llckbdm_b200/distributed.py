@@ -1,94 +1,156 @@
 """Multi-GPU ensemble solve: one process per GPU (torch.distributed), members sharded by cost.
 
 Ensemble members are independent (reference llckbdm/sampling.py:52 has no cross-iteration state), so
-the data path needs NO collective: each rank solves its LPT shard.  The single exchange step is one
-``all_gather`` of fixed-stride result buffers so that every rank holds the complete, ``m_range``-ordered
-line lists for the host-side clustering (reference llckbdm/llckbdm.py:94-124).  With the NCCL backend
-the gather runs over NVLink 5 / NVSwitch on device tensors; the gloo backend (CPU tensors) is used
-by the CPU tests, which inject a solver stub.
+the data path needs NO collective: each rank uploads only the FIDs of its own longest-processing-time-first
+shard and solves it in memory-sized chunks (``ensemble.solve_chunks``).  The single exchange step is one
+``all_gather`` of the fixed-stride result buffer (line lists + singular values + int32 n_valid/status packed
+into one byte buffer per rank) so that every rank holds the complete, ``m_range``-ordered line lists for the
+clustering stage (reference llckbdm/llckbdm.py:94-124).  With the NCCL backend the gather runs over
+NVLink 5 / NVSwitch on device tensors and the gathered buffer comes back to the host in ONE copy; the gloo
+backend (CPU tensors) is used by the CPU tests, which inject a solver stub.
 """
 import numpy as np
 
-from .ensemble import flops_per_solve, lpt_shards, solve_device, flatten_signals
+from .ensemble import flops_per_solve, lpt_shards, solve_chunks, flatten_signals, to_device_complex
 
 
-def _pack(line_lists, sing_vals, n_valid, status, lmax, mmax, count, torch, device):
-    """Fixed-stride per-rank buffer: [count, lmax*4 + mmax + 2] float64 (status and n_valid stored as doubles)."""
-    width = lmax * 4 + mmax + 2
-    buf = torch.zeros((count, width), dtype=torch.float64, device=device)
-    k = line_lists.shape[0]
-    if k:
-        buf[:k, :line_lists.shape[1] * 4] = line_lists.reshape(k, -1)
-        buf[:k, lmax * 4:lmax * 4 + sing_vals.shape[1]] = sing_vals
-        buf[:k, lmax * 4 + mmax] = n_valid.to(torch.float64)
-        buf[:k, lmax * 4 + mmax + 1] = status.to(torch.float64)
+def record_bytes(lmax, mmax):
+    """Bytes of one member's fixed-stride record: line list [lmax, 4] f64 | singular values [mmax] f64 | n_valid, status int32."""
+    return 8 * (4 * lmax + mmax) + 8
+
+
+def shard_signals(flat, offsets, lens, mine, shared):
+    """The part of the FID buffer a rank has to upload: the one shared FID, or only its own members' FIDs re-packed."""
+    if shared or len(mine) == 0:
+        return flat if shared else flat[:0], offsets[mine], lens[mine]
+    parts = [flat[offsets[i]:offsets[i] + lens[i]] for i in mine]
+    new_len = lens[mine]
+    new_off = np.concatenate(([0], np.cumsum(new_len)[:-1])).astype(np.int64)
+    return np.concatenate(parts), new_off, new_len
+
+
+def _pack_into(buf, rows, r, lmax, mmax, torch):
+    """Write one chunk's results into rows ``rows`` of the rank's record buffer (uint8 [count, record_bytes])."""
+    k = len(rows)
+    f64 = buf.view(torch.float64).view(buf.shape[0], -1)          # [count, 4 lmax + mmax + 1]
+    i32 = buf.view(torch.int32).view(buf.shape[0], -1)            # [count, 2 (4 lmax + mmax) + 2]
+    rows_t = torch.as_tensor(rows, dtype=torch.int64, device=buf.device)
+    ll = r["line_lists"].reshape(k, -1)
+    f64[rows_t, :ll.shape[1]] = ll
+    f64[rows_t, 4 * lmax:4 * lmax + r["sing_vals"].shape[1]] = r["sing_vals"]
+    i32[rows_t, 2 * (4 * lmax + mmax)] = r["n_valid"].to(torch.int32)
+    i32[rows_t, 2 * (4 * lmax + mmax) + 1] = r["status"].to(torch.int32)
+
+
+class ShardPlan:
+    """Longest-processing-time-first assignment of the members to the ranks + the geometry of the gathered record buffer."""
+
+    def __init__(self, m, l, world, rank):
+        self.m = np.asarray(m, dtype=np.int32)
+        self.l = np.asarray(l, dtype=np.int32)
+        self.M = len(self.m)
+        self.world, self.rank = world, rank
+        self.shards = lpt_shards([flops_per_solve(mi, li) for mi, li in zip(self.m, self.l)], world)
+        self.mine = np.asarray(self.shards[rank], dtype=np.int64)
+        self.count = max(len(s) for s in self.shards)
+        self.mmax, self.lmax = int(self.m.max()), int(self.l.max())
+        self.rec = record_bytes(self.lmax, self.mmax)
+
+
+def plan_shards(m, l, group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return ShardPlan(m, l, dist.get_world_size(group), dist.get_rank(group))
+    return ShardPlan(m, l, 1, 0)
+
+
+def solve_shard_device(plan, sig_dev, my_off, my_len, p, q, dwell, chunk=None, buf=None, flags=0, infos=None):
+    """This rank's shard, FIDs already on the device: chunked batched solves whose results are packed into the rank's record
+    buffer (uint8 [count, rec], device).  Enqueue only -- nothing here waits for the stream."""
+    import torch
+    dev = sig_dev.device
+    if buf is None:
+        buf = torch.zeros((plan.count, plan.rec), dtype=torch.uint8, device=dev)
+    if len(plan.mine):
+        for rows, r in solve_chunks(sig_dev, my_off, my_len, plan.m[plan.mine], plan.l[plan.mine], p, q, dwell, chunk=chunk,
+                                    want_mu=False, flags=flags):
+            _pack_into(buf, np.asarray(rows), r, plan.lmax, plan.mmax, torch)
+            if infos is not None:
+                infos.append((len(rows), r["info"]))
     return buf
 
 
-def solve_ensemble_distributed(signals, m, l, p, q, dwell, group=None, local_solver=None, device=None):
-    """Sharded ensemble solve.  Every rank passes the SAME arguments; every rank returns the full result
-    (line_lists float64[M,lmax,4], sing_vals float64[M,mmax], n_valid int[M], status int[M]) in member order.
-
-    local_solver(signals_flat, offsets, m, l, p, q, dwell) -> dict of torch tensors is injectable for CPU tests.
-    """
+def gather_records(plan, buf, group=None):
+    """The ONE exchange step: all_gather of every rank's record buffer -> [world, count, rec] on every rank."""
     import torch
     import torch.distributed as dist
-    M = len(m)
-    m = np.asarray(m, dtype=np.int32)
-    l = np.asarray(l, dtype=np.int32)
-    if dist.is_available() and dist.is_initialized():
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-    else:
-        world, rank = 1, 0
-    shards = lpt_shards([flops_per_solve(mi, li) for mi, li in zip(m, l)], world)
-    mine = np.asarray(shards[rank], dtype=np.int64)
-    count = max(len(s) for s in shards)
-    mmax, lmax = int(m.max()), int(l.max())
-    flat, offsets = flatten_signals(signals, M)
-    if local_solver is None:
-        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        sig_dev = torch.from_numpy(flat.view(np.float64)).to(dev).view(torch.complex128)
+    if plan.world == 1:
+        return buf.unsqueeze(0)
+    gathered = torch.empty((plan.world, plan.count, plan.rec), dtype=torch.uint8, device=buf.device)
+    dist.all_gather(list(gathered.unbind(0)), buf, group=group)
+    return gathered
 
-        def local_solver(idx):
-            return solve_device(sig_dev, offsets[idx], m[idx], l[idx], p, q, dwell, want_mu=False)
-    else:
-        dev = torch.device("cpu") if device is None else torch.device(device)
-        user_solver = local_solver
 
-        def local_solver(idx):
-            return user_solver(flat, offsets[idx], m[idx], l[idx], p, q, dwell)
-    if len(mine):
-        r = local_solver(mine)
-        buf = _pack(r["line_lists"], r["sing_vals"], r["n_valid"], r["status"], lmax, mmax, count, torch, dev)
-    else:
-        buf = torch.zeros((count, lmax * 4 + mmax + 2), dtype=torch.float64, device=dev)
-    if world > 1:
-        gathered = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(gathered, buf, group=group)          # the ONE exchange step
-    else:
-        gathered = [buf]
-    out_ll = np.zeros((M, lmax, 4))
-    out_sv = np.zeros((M, mmax))
-    out_nv = np.zeros(M, dtype=np.int32)
-    out_st = np.zeros(M, dtype=np.int32)
-    for rk, idx in enumerate(shards):
+def unpack_records(plan, gathered_host):
+    """Host copy of the gathered records -> member-ordered arrays."""
+    lmax, mmax = plan.lmax, plan.mmax
+    f64 = gathered_host.view(np.float64).reshape(plan.world, plan.count, -1)
+    i32 = gathered_host.view(np.int32).reshape(plan.world, plan.count, -1)
+    out_ll = np.zeros((plan.M, lmax, 4))
+    out_sv = np.zeros((plan.M, mmax))
+    out_nv = np.zeros(plan.M, dtype=np.int32)
+    out_st = np.zeros(plan.M, dtype=np.int32)
+    for rk, idx in enumerate(plan.shards):
         if not idx:
             continue
-        g = gathered[rk][:len(idx)].cpu().numpy()
-        out_ll[idx] = g[:, :lmax * 4].reshape(len(idx), lmax, 4)
-        out_sv[idx] = g[:, lmax * 4:lmax * 4 + mmax]
-        out_nv[idx] = g[:, lmax * 4 + mmax].astype(np.int32)
-        out_st[idx] = g[:, lmax * 4 + mmax + 1].astype(np.int32)
-    return dict(line_lists=out_ll, sing_vals=out_sv, n_valid=out_nv, status=out_st, shards=shards)
+        k = len(idx)
+        out_ll[idx] = f64[rk, :k, :4 * lmax].reshape(k, lmax, 4)
+        out_sv[idx] = f64[rk, :k, 4 * lmax:4 * lmax + mmax]
+        out_nv[idx] = i32[rk, :k, 2 * (4 * lmax + mmax)]
+        out_st[idx] = i32[rk, :k, 2 * (4 * lmax + mmax) + 1]
+    return dict(line_lists=out_ll, sing_vals=out_sv, n_valid=out_nv, status=out_st, shards=plan.shards)
+
+
+def solve_ensemble_distributed(signals, m, l, p, q, dwell, group=None, local_solver=None, device=None, chunk=None, stats=None):
+    """Sharded ensemble solve.  Every rank passes the SAME arguments; every rank returns the full result
+    (line_lists float64[M,lmax,4], sing_vals float64[M,mmax], n_valid int32[M], status int32[M]) in member order.
+
+    local_solver(signals_flat, offsets, lens, m, l, p, q, dwell) -> iterator of (local indices, dict of torch tensors) is
+    injectable for CPU tests (it replaces the chunked device solve).  ``stats`` (dict, optional) receives the shard sizes, the
+    bytes each rank contributes to the all_gather and the bytes uploaded / downloaded by this rank.
+    """
+    import torch
+    plan = plan_shards(m, l, group)
+    flat, offsets, lens = flatten_signals(signals, plan.M)
+    shared = isinstance(signals, np.ndarray) and signals.ndim == 1
+    my_flat, my_off, my_len = shard_signals(flat, offsets, lens, plan.mine, shared)
+    if local_solver is None:
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(dev):
+            sig_dev = to_device_complex(my_flat, dev) if len(plan.mine) else torch.zeros(1, dtype=torch.complex128, device=dev)
+            buf = solve_shard_device(plan, sig_dev, my_off, my_len, p, q, dwell, chunk=chunk)
+    else:
+        dev = torch.device("cpu") if device is None else torch.device(device)
+        buf = torch.zeros((plan.count, plan.rec), dtype=torch.uint8, device=dev)
+        if len(plan.mine):
+            for rows, r in local_solver(my_flat, my_off, my_len, plan.m[plan.mine], plan.l[plan.mine], p, q, dwell):
+                _pack_into(buf, np.asarray(rows), r, plan.lmax, plan.mmax, torch)
+    gathered = gather_records(plan, buf, group)
+    out = unpack_records(plan, gathered.cpu().numpy())                       # ONE device-to-host copy
+    if stats is not None:
+        stats.update(world=plan.world, shard_sizes=[len(s) for s in plan.shards], allgather_bytes_per_rank=int(plan.count * plan.rec),
+                     h2d_bytes=int(my_flat.size * 16), d2h_bytes=int(plan.world * plan.count * plan.rec))
+    return out
 
 
 def sample_kbdm_distributed(data, dwell, m_range, p, l, q=0, filter_invalid_features=True, group=None):
-    """``sampling.sample_kbdm`` with the members sharded over the ranks of ``group`` (same return contract)."""
-    from .kbdm import KbdmInfo, raise_for_status, resolve_m_l
+    """``sampling.sample_kbdm`` with the members sharded over the ranks of ``group`` (same return contract, same errors)."""
+    from .kbdm import KbdmInfo, check_finite, raise_for_status, resolve_m_l
     from .sampling import filter_samples
     ms, ls = [], []
     for mm in m_range:
         a, b = resolve_m_l(data.size, mm, l, p)
+        check_finite(data, a, p)
         ms.append(a)
         ls.append(b)
     if not ms:

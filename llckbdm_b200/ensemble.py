@@ -63,15 +63,69 @@ def max_chunk(ld, device=None, reserve_frac=0.8, flags=0):
     """Largest number of members of leading dimension ld whose workspace fits in free HBM."""
     torch = _require_cuda()
     free, _total = torch.cuda.mem_get_info(device)
+    # blocks torch's caching allocator holds but has not handed out (e.g. the workspace of the previous call) are reusable
+    free += max(0, torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device))
     lib = _native.load()
     per = lib.llck_workspace_bytes(1, ld, flags)
     return max(1, int(free * reserve_frac // per))
 
 
-def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=None, stream=None, want_mu=True):
-    """Run llck_kbdm_batched on device-resident signals.
+def plan_chunks(M, cap, wave=148):
+    """Chunk size for M members when at most ``cap`` fit in memory: as few chunks as possible, of equal size, rounded up to a
+    whole number of waves of the one-CTA-per-member kernels (``wave`` = SM count) so that no chunk ends in a nearly empty wave."""
+    cap = max(1, int(cap))
+    if M <= cap:
+        return M
+    nchunks = -(-M // cap)
+    size = -(-M // nchunks)
+    if wave > 0 and size > wave:
+        rounded = -(-size // wave) * wave
+        if rounded <= cap:
+            size = rounded
+        elif (cap // wave) * wave > 0:
+            size = (cap // wave) * wave
+    return min(size, cap)
 
-    signals_dev: torch complex128 CUDA tensor (flat); sig_offset/m/l: host int sequences (one per member).
+
+def sm_count(device=None):
+    torch = _require_cuda()
+    return torch.cuda.get_device_properties(torch.cuda.current_device() if device is None else device).multi_processor_count
+
+
+def solve_chunks(sig_dev, offsets, lens, m, l, p, q, dwell, chunk=None, want_mu=True, flags=0, options=None, order=None):
+    """Generator over cost-sorted chunks of an ensemble whose FIDs are already on the device: yields (idx, result) with ``idx`` the
+    member indices of the chunk and ``result`` the dict of ``solve_device`` (device tensors, valid until the next iteration: the
+    workspace is reused).  ``chunk=None`` sizes the chunks to the free HBM, rounded to whole waves (``plan_chunks``)."""
+    torch = _require_cuda()
+    lib = _native.load()
+    m = np.asarray(m, dtype=np.int32)
+    l = np.asarray(l, dtype=np.int32)
+    M = len(m)
+    if M == 0:
+        return
+    dev = sig_dev.device
+    if chunk is None:
+        ld = lib.llck_leading_dim(int(m.max()))
+        chunk = plan_chunks(M, max_chunk(ld, dev, flags=flags), sm_count(dev))
+    if order is None:
+        # cost-sorted chunks keep similar sizes together (less padding work inside a launch); one chunk keeps the caller's order
+        order = np.arange(M) if chunk >= M else np.argsort(-(m.astype(np.int64) * 4096 + l), kind="stable")
+    ws = None
+    for c0 in range(0, M, chunk):
+        idx = order[c0:c0 + chunk]
+        r = solve_device(sig_dev, offsets[idx], m[idx], l[idx], p, q, dwell, flags=flags, workspace=ws, want_mu=want_mu,
+                         sig_len=lens[idx], options=options)
+        ws = r["workspace"]
+        yield idx, r
+
+
+def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=None, stream=None, want_mu=True,
+                 sig_len=None, options=None):
+    """Enqueue llck_kbdm_batched on device-resident signals; ASYNCHRONOUS (returns before the stream drains).
+
+    signals_dev: torch complex128 CUDA tensor (flat); sig_offset/m/l: host int sequences (one per member);
+    sig_len: points of each member's FID (default: everything from its offset to the end of ``signals_dev``);
+    options: ``_native.Options`` (explicit tuning knobs) or None.
     Returns dict of torch CUDA tensors (line_lists, mu, D, sing_vals, n_valid, status) + info list + workspace.
     """
     torch = _require_cuda()
@@ -81,7 +135,13 @@ def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=
     m_arr = np.ascontiguousarray(m, dtype=np.int32)
     l_arr = np.ascontiguousarray(l, dtype=np.int32)
     off_arr = np.ascontiguousarray(sig_offset, dtype=np.int64)
+    if sig_len is None:
+        len_arr = int(signals_dev.numel()) - off_arr
+    else:
+        len_arr = np.ascontiguousarray(sig_len, dtype=np.int64)
     mmax, lmax = int(m_arr.max()), int(l_arr.max())
+    if mmax > _native.M_MAX:
+        _native.check_rc(_native.E_TOO_LARGE, "llck_kbdm_batched")
     ld = lib.llck_leading_dim(mmax)
     need = lib.llck_workspace_bytes(batch, ld, flags)
     if workspace is None or workspace.numel() < need:
@@ -96,13 +156,14 @@ def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     rc = lib.llck_kbdm_batched(
         signals_dev.data_ptr(), off_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+        len_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
         m_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), l_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
         int(p), float(q), float(dwell), batch,
         line_lists.data_ptr(), lmax * 4,
         mu.data_ptr() if want_mu else None, D.data_ptr() if want_mu else None, lmax,
         sv.data_ptr(), mmax,
         n_valid.data_ptr(), status.data_ptr(),
-        workspace.data_ptr(), need, int(flags),
+        workspace.data_ptr(), need, int(flags), ctypes.byref(options) if options is not None else None,
         st.cuda_stream, info)
     _native.check_rc(rc, "llck_kbdm_batched")
     return dict(line_lists=line_lists, mu=mu, D=D, sing_vals=sv, n_valid=n_valid, status=status,
@@ -142,13 +203,13 @@ def score_candidates(data, dwell, candidates, filter_rows=False, device=None):
         if rows[i] > 0:
             packed[i, :rows[i]] = np.asarray(c, dtype=np.float64).reshape(-1, 4)
     with torch.cuda.device(dev):
-        d_dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.complex128).view(np.float64)).to(dev).view(torch.complex128)
+        d_dev = to_device_complex(np.asarray(data).ravel(), dev)
         out = score_rmse_device(d_dev, dwell, torch.from_numpy(packed).to(dev), torch.from_numpy(rows).to(dev), filter_rows=filter_rows)
         return [float(x) for x in out.cpu().numpy()]
 
 
 def solve_pooled(signal, m, l, p, q, dwell, device=None, chunk=None, amplitude_tol=1e-6):
-    """Solve an ensemble on ONE shared FID and return the pooled, filtered line lists and their clustering features, both
+    """Solve an ensemble on ONE shared FID (host array or complex128 CUDA tensor) and return the pooled, filtered line lists and their clustering features, both
     produced on the device from the solver's output buffer (llck_pool_features; replaces the host concatenate / filter_samples /
     _transform_line_lists of reference llckbdm.py:94-98).
 
@@ -158,22 +219,18 @@ def solve_pooled(signal, m, l, p, q, dwell, device=None, chunk=None, amplitude_t
     lib = _native.load()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     M = len(m)
+    if M == 0:
+        return np.zeros((0, 4)), np.zeros((0, 4)), np.zeros(0, dtype=np.int32)
     m = np.asarray(m, dtype=np.int32)
     l = np.asarray(l, dtype=np.int32)
-    ld = lib.llck_leading_dim(int(m.max()))
-    flat = np.ascontiguousarray(signal, dtype=np.complex128)
     status = np.zeros(M, dtype=np.int32)
     per_member = [None] * M
+    if isinstance(signal, torch.Tensor):          # FID already resident on the device (iterative_llc_kbdm keeps the residual there)
+        dev = signal.device
     with torch.cuda.device(dev):
-        if chunk is None:
-            chunk = min(M, max_chunk(ld, dev))
-        sig_dev = torch.from_numpy(flat.view(np.float64)).to(dev).view(torch.complex128)
-        order = np.arange(M) if chunk >= M else np.argsort(-(m.astype(np.int64) * 4096 + l), kind="stable")
-        ws = None
-        for c0 in range(0, M, chunk):
-            idx = order[c0:c0 + chunk]
-            r = solve_device(sig_dev, np.zeros(len(idx), dtype=np.int64), m[idx], l[idx], p, q, dwell, workspace=ws, want_mu=False)
-            ws = r["workspace"]
+        sig_dev = signal.reshape(-1) if isinstance(signal, torch.Tensor) else to_device_complex(np.asarray(signal).ravel(), dev)
+        offsets, lens = np.zeros(M, dtype=np.int64), np.full(M, int(sig_dev.numel()), dtype=np.int64)
+        for idx, r in solve_chunks(sig_dev, offsets, lens, m, l, p, q, dwell, chunk=chunk, want_mu=False):
             counts = r["n_valid"].to(torch.int64)
             offs = torch.cumsum(counts, 0) - counts
             total = int(counts.sum().item())
@@ -189,8 +246,6 @@ def solve_pooled(signal, m, l, p, q, dwell, device=None, chunk=None, amplitude_t
             cuts = np.cumsum(counts.cpu().numpy())[:-1]
             for k, (sp, fp) in zip(idx, zip(np.split(s_h, cuts), np.split(f_h, cuts))):
                 per_member[k] = (sp, fp)
-    if M == 0:
-        return np.zeros((0, 4)), np.zeros((0, 4)), status
     return (np.concatenate([pm[0] for pm in per_member]), np.concatenate([pm[1] for pm in per_member]), status)
 
 
@@ -265,18 +320,25 @@ def silhouette_samples_device(features, labelings, device=None):
 
 
 def flatten_signals(signals, M):
-    """One shared 1-D FID, or a list of M FIDs -> (flat complex128 array, int64 offsets)."""
+    """One shared 1-D FID, or a list of M FIDs -> (flat complex128 array, int64 offsets, int64 lengths)."""
     if isinstance(signals, np.ndarray) and signals.ndim == 1:
-        return np.ascontiguousarray(signals, dtype=np.complex128), np.zeros(M, dtype=np.int64)
-    sigs = [np.ascontiguousarray(s, dtype=np.complex128) for s in signals]
+        return (np.ascontiguousarray(signals, dtype=np.complex128), np.zeros(M, dtype=np.int64),
+                np.full(M, signals.size, dtype=np.int64))
+    sigs = [np.ascontiguousarray(s, dtype=np.complex128).ravel() for s in signals]
     if len(sigs) != M:
         raise ValueError("need one signal per member")
     lens = np.array([len(s) for s in sigs], dtype=np.int64)
     offsets = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int64)
-    return np.concatenate(sigs), offsets
+    return np.concatenate(sigs), offsets, lens
 
 
-def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None, score_rmse=False):
+def to_device_complex(flat, dev):
+    """Host complex128 array -> flat device tensor (one H2D copy)."""
+    torch = _require_cuda()
+    return torch.from_numpy(np.ascontiguousarray(flat, dtype=np.complex128).view(np.float64)).to(dev).view(torch.complex128)
+
+
+def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None, score_rmse=False, options=None):
     """Solve an ensemble given HOST inputs; returns an ``EnsembleResult`` of host arrays.
 
     signals: either one 1-D complex array shared by all members, or a list of 1-D complex arrays (one per member).
@@ -287,16 +349,16 @@ def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None, score_rm
     torch = _require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     M = len(m)
-    flat, offsets = flatten_signals(signals, M)
+    flat, offsets, lens = flatten_signals(signals, M)
     m = np.asarray(m, dtype=np.int32)
     l = np.asarray(l, dtype=np.int32)
     mmax, lmax = int(m.max()), int(l.max())
     lib = _native.load()
     ld = lib.llck_leading_dim(mmax)
+    if score_rmse and not (isinstance(signals, np.ndarray) and signals.ndim == 1):
+        raise ValueError("score_rmse needs one shared FID")
     with torch.cuda.device(dev):
-        if chunk is None:
-            chunk = min(M, max_chunk(ld, dev))
-        sig_dev = torch.from_numpy(flat.view(np.float64)).to(dev).view(torch.complex128)
+        sig_dev = to_device_complex(flat, dev)
         out_ll = np.zeros((M, lmax, 4))
         out_mu = np.zeros((M, lmax), dtype=np.complex128)
         out_D = np.zeros((M, lmax), dtype=np.complex128)
@@ -304,16 +366,8 @@ def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None, score_rm
         out_nv = np.zeros(M, dtype=np.int32)
         out_st = np.zeros(M, dtype=np.int32)
         out_rm = np.full(M, np.inf) if score_rmse else None
-        if score_rmse and not (isinstance(signals, np.ndarray) and signals.ndim == 1):
-            raise ValueError("score_rmse needs one shared FID")
-        ws = None
         infos = []
-        # cost-sorted chunks keep similar sizes together (less padding work inside a launch)
-        order = np.argsort(-(m.astype(np.int64) * 4096 + l), kind="stable")
-        for c0 in range(0, M, chunk):
-            idx = order[c0:c0 + chunk]
-            r = solve_device(sig_dev, offsets[idx], m[idx], l[idx], p, q, dwell, workspace=ws)
-            ws = r["workspace"]
+        for idx, r in solve_chunks(sig_dev, offsets, lens, m, l, p, q, dwell, chunk=chunk, options=options):
             lm, mm = r["line_lists"].shape[1], r["sing_vals"].shape[1]
             out_ll[idx, :lm] = r["line_lists"].cpu().numpy()
             out_mu[idx, :lm] = r["mu"].cpu().numpy()

@@ -2,6 +2,7 @@
 the solve itself is one call of the CUDA batched solver (batch of one)."""
 import logging
 
+import attr
 import numpy as np
 
 from . import _native
@@ -10,20 +11,14 @@ from .ensemble import solve_ensemble
 logger = logging.getLogger(__name__)
 
 
+@attr.s
 class KbdmInfo:
-    """Record returned next to the line list (reference kbdm.py:10-16): m, l, p, q, singular_values (length m)."""
-
-    __slots__ = ("m", "l", "p", "q", "singular_values")
-
-    def __init__(self, m, l, p, q, singular_values):
-        self.m = m
-        self.l = l
-        self.p = p
-        self.q = q
-        self.singular_values = singular_values
-
-    def __repr__(self):
-        return f"KbdmInfo(m={self.m}, l={self.l}, p={self.p}, q={self.q}, singular_values=<{len(self.singular_values)}>)"
+    """Record returned next to the line list (reference kbdm.py:10-16): the same attrs class, singular_values has length m."""
+    m = attr.ib()
+    l = attr.ib()
+    p = attr.ib()
+    q = attr.ib()
+    singular_values = attr.ib()
 
 
 def resolve_m_l(data_size, m, l, p):
@@ -39,6 +34,8 @@ def resolve_m_l(data_size, m, l, p):
     m_max = (data_size + 1 - p) / 2
     if m > m_max or l > m_max:
         raise ValueError("m or l can't be greater than (n + 1 - p)/2.")
+    if m > _native.M_MAX:          # limit of this implementation (LLCK_M_MAX, include/llck.h); the reference has none
+        raise ValueError(f"m = {int(m)} is above the largest Hankel dimension the CUDA solver supports ({_native.M_MAX})")
     return int(m), int(l)
 
 

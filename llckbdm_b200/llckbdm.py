@@ -1,60 +1,126 @@
 """Drop-in for reference llckbdm/llckbdm.py (LLC-KBDM driver).
 
 The ensemble of KBDM solves (79 % of the reference's wall time) runs on the GPU
-through ``sampling.sample_kbdm``.  Of the clustering stage ("next" row f-1 of the scope table) the two O(n^2)/O(M n K) loops
-are on the GPU too: the silhouette coefficients of all clusterings (one batched ``llck_silhouette_batched`` launch instead of
-M-1 ``sklearn.metrics.silhouette_samples`` calls, llckbdm.py:291) and the min-RMSE scoring of the cluster averages
-(``llck_rmse_batched``, llckbdm.py:120), and so are the two O(n^2) stages of the HDBSCAN fits (core distances and Prim's spanning
-tree of the mutual-reachability graph, for all min_samples values in one launch each, edge-for-edge identical to the host
-clusterer's); the tree condensation / EOM selection stays the clusterer's own host code, so labels agree exactly.
+through ``sampling.sample_kbdm_pooled``.  The clustering stage ("next" row f-1 of the scope table) is accelerated too: the
+silhouette coefficients of all clusterings (one batched ``llck_silhouette_batched`` launch instead of M-1
+``sklearn.metrics.silhouette_samples`` calls, llckbdm.py:291), the min-RMSE scoring of the cluster averages
+(``llck_rmse_batched``, llckbdm.py:120), the two O(n^2) stages of the HDBSCAN fits (core distances and Prim's spanning
+tree of the mutual-reachability graph, for all min_samples values in one launch each) and the rest of every fit (dendrogram,
+condensed tree, excess-of-mass selection: ``llck_hdbscan_labels``, all fits on native host threads).
 
-Clusterer: the reference imports the un-vendored ``hdbscan`` package (llckbdm.py:3).  If it is
-importable it is used; otherwise ``sklearn.cluster.HDBSCAN`` with the same defaults
-(min_cluster_size=5, euclidean, EOM, allow_single_cluster=False) stands in.
+Clusterer contract.  The reference imports the un-vendored ``hdbscan`` package (llckbdm.py:3) and calls
+``hdbscan.HDBSCAN(min_samples=k)`` with every other parameter at its default (min_cluster_size=5, euclidean, EOM,
+allow_single_cluster=False).  ``hdbscan`` does NOT count the point itself among its ``min_samples`` neighbours;
+``sklearn.cluster.HDBSCAN`` (derived from it, the stand-in here) does, so the reference's ``min_samples=k`` is
+``sklearn.cluster.HDBSCAN(min_samples=k+1)`` and, on the device, the distance to the (k+1)-th nearest neighbour including the
+point itself.  ``k`` is clipped to n-1 like ``hdbscan`` does.  The device path is the default whether or not ``hdbscan`` is
+importable; it computes the EXACT minimum spanning tree, while ``hdbscan``'s default ``approx_min_span_tree=True`` Boruvka may
+return a slightly different tree -- label parity is therefore pinned against sklearn's exact-tree implementation (bit-identical
+edges, identical labels), not against the absent package.  ``CLUSTER_BACKEND = "host"`` runs the plain library fits
+(``hdbscan`` if importable, else sklearn with k+1) instead.
 """
 import logging
 import os
+from concurrent.futures import ThreadPoolExecutor
 
+import attr
 import numpy as np
 
-from .metrics import calculate_freq_domain_rmse
-from .min_rmse_kbdm import min_rmse_kbdm
+from . import _native
+from .ensemble import (hdbscan_msts_device, score_rmse_device, silhouette_samples_device, solve_pooled, to_device_complex,
+                       _require_cuda)
+from .kbdm import check_finite, raise_for_status, resolve_m_l
+from .metrics import calculate_freq_domain_rmse  # noqa: F401
+from .min_rmse_kbdm import min_rmse_kbdm  # noqa: F401
 from .sampling import filter_samples, sample_kbdm, sample_kbdm_pooled  # noqa: F401
-from .ensemble import hdbscan_msts_device, silhouette_samples_device
-from .sig_gen import gen_t_freq_arrays, multi_fid, multi_fid_batched_device  # noqa: F401
+from .sig_gen import _validate_parameters, gen_t_freq_arrays, multi_fid, multi_fid_batched_device  # noqa: F401
 
 logger = logging.getLogger(__name__)
 
 try:  # pragma: no cover - depends on the environment
     from hdbscan import HDBSCAN as _HDBSCAN
+    _HDBSCAN_COUNTS_SELF = False
 except Exception:  # noqa: BLE001
     from sklearn.cluster import HDBSCAN as _HDBSCAN
+    _HDBSCAN_COUNTS_SELF = True
+
+# "device": spanning trees on the GPU + native labelling (default); "host": the clustering library's own fits
+CLUSTER_BACKEND = "device"
+# worker threads / processes of the host halves (0 = all cores)
+CLUSTER_JOBS = 0
+MIN_CLUSTER_SIZE = 5           # hdbscan.HDBSCAN default, never changed by the reference
 
 
+@attr.s(auto_attribs=True)
 class LlcKbdmResult:
-    def __init__(self, line_list=None, rmse=None, silhouette=None):
-        self.line_list = np.array([]) if line_list is None else line_list
-        self.rmse = rmse
-        self.silhouette = np.array([]) if silhouette is None else silhouette
+    line_list: np.ndarray = np.array([])
+    rmse: float = None
+    silhouette: np.ndarray = np.array([])
 
 
+@attr.s(auto_attribs=True)
 class IterativeLlcKbdmResult:
-    def __init__(self, line_list=None, line_lists=None, rmse=None, silhouettes=None):
-        self.line_list = np.array([]) if line_list is None else line_list
-        self.line_lists = np.array([]) if line_lists is None else line_lists
-        self.rmse = rmse
-        self.silhouettes = np.array([]) if silhouettes is None else silhouettes
+    line_list: np.ndarray = np.array([])
+    line_lists: np.ndarray = np.array([])
+    rmse: float = None
+    silhouettes: np.ndarray = np.array([])
 
 
+@attr.s(auto_attribs=True)
 class ClusteringResult:
-    def __init__(self, num_clusters=0, labels=None, clustered=None, non_clustered=None, summarized_line_list=None,
-                 clustered_silhouettes=None):
-        self.num_clusters = num_clusters
-        self.labels = np.array([]) if labels is None else labels
-        self.clustered = [] if clustered is None else clustered
-        self.non_clustered = np.array([]) if non_clustered is None else non_clustered
-        self.summarized_line_list = np.array([]) if summarized_line_list is None else summarized_line_list
-        self.clustered_silhouettes = np.array([]) if clustered_silhouettes is None else clustered_silhouettes
+    num_clusters: int = 0
+    labels: np.ndarray = np.array([])
+    clustered: np.ndarray = np.array([])
+    non_clustered: np.ndarray = np.array([])
+    summarized_line_list: np.ndarray = np.array([])
+    clustered_silhouettes: np.ndarray = np.array([])
+
+
+def _resolve_members(n_points, m_range, l, p):
+    ms, ls = [], []
+    for m in m_range:
+        logger.info(f'Computing KBDM with m = {m}')
+        mm, ll_ = resolve_m_l(n_points, m, l, p)
+        ms.append(mm)
+        ls.append(ll_)
+    return ms, ls
+
+
+def _llc_kbdm_device(sig_dev, dwell, ms, ls, p, q):
+    """``llc_kbdm`` on an FID that is already on the device (torch complex128 CUDA tensor): batched solves, pooling + filter +
+    feature transform, spanning trees, silhouettes and the min-RMSE selection all read it there; only line lists, labels and
+    silhouettes (kilobytes) cross to the host."""
+    torch = _require_cuda()
+    if q > 0:
+        logger.debug('Using Tikhonov Regularization with q=%f', q)
+    # sampling + pooling + filter + feature transform (reference llckbdm.py:76-98) in one device pass
+    samples, features, status = solve_pooled(sig_dev, ms, ls, p, q, dwell)
+    for k, mm in enumerate(ms):
+        raise_for_status(int(status[k]), mm)
+    if len(samples) == 0:
+        return LlcKbdmResult()
+    # HDBSCAN for min_samples = 1..M-1 (reference llckbdm.py:104-116): all fits at once
+    labelings = _fit_all(features, list(range(1, len(ms))))
+    results = _results_from_labelings(samples, features, labelings)
+    if not results:
+        return LlcKbdmResult()
+    # min-RMSE selection over the cluster averages (reference llckbdm.py:120-124 -> min_rmse_kbdm.py:33-55) on the device
+    cands = [r.summarized_line_list for r in results]
+    for cand in cands:                    # the reference's multi_fid validates every row (sig_gen.py:140-169)
+        for row in cand:
+            _validate_parameters(*row)
+    rows = np.array([len(c) for c in cands], dtype=np.int32)
+    packed = np.zeros((len(cands), max(1, int(rows.max())), 4))
+    for i, c in enumerate(cands):
+        packed[i, :rows[i]] = c
+    dev = sig_dev.device
+    with torch.cuda.device(dev):
+        rmses = score_rmse_device(sig_dev, dwell, torch.from_numpy(packed).to(dev), torch.from_numpy(rows).to(dev),
+                                  filter_rows=False).cpu().numpy()
+    for i, rmse in enumerate(rmses):
+        logger.debug('RMSE for sample #%d: %f', i, rmse)
+    k = int(np.argmin(rmses))
+    return LlcKbdmResult(line_list=cands[k], rmse=float(rmses[k]), silhouette=np.array(results[k].clustered_silhouettes))
 
 
 def llc_kbdm(data, dwell, m_range, p=1, l=None, q=0.0):
@@ -63,41 +129,46 @@ def llc_kbdm(data, dwell, m_range, p=1, l=None, q=0.0):
     clustering whose averaged line list has the smallest frequency-domain RMSE."""
     if len(m_range) < 2:
         raise ValueError("size of 'm_range' must be greater than 2.")
-    # sampling + pooling + filter + feature transform (reference llckbdm.py:76-98) in one device pass
-    samples, features = sample_kbdm_pooled(data=data, dwell=dwell, m_range=m_range, p=p, l=l, q=q)
-    if len(samples) == 0:
-        return LlcKbdmResult()
-    n_members = len(m_range)
-    # HDBSCAN for min_samples = 1..M-1 (reference llckbdm.py:104-116): the fits are independent -> spread over the host cores;
-    # the silhouettes of all clusterings are then ONE batched device launch instead of M-1 O(n^2) sklearn calls.
-    labelings = _fit_all(features, list(range(1, n_members)))
-    results = _results_from_labelings(samples, features, labelings)
-    best = min_rmse_kbdm(data=data, dwell=dwell, samples=[r.summarized_line_list for r in results])
-    if best is None:
-        return LlcKbdmResult()
-    return LlcKbdmResult(line_list=best.line_list, rmse=best.min_rmse,
-                         silhouette=np.array(results[best.min_index].clustered_silhouettes))
+    torch = _require_cuda()
+    ms, ls = _resolve_members(data.size, m_range, l, p)
+    for mm in ms:
+        check_finite(data, mm, p)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return _llc_kbdm_device(to_device_complex(np.asarray(data).ravel(), dev), dwell, ms, ls, p, q)
 
 
 def iterative_llc_kbdm(data, dwell, m_range, p=1, l=None, q=0.0, max_iterations=5, silhouette_threshold=0.6):
-    """Residual-iteration variant (reference llckbdm.py:144-199)."""
+    """Residual-iteration variant (reference llckbdm.py:144-199).  The FID goes to the device ONCE; the running estimate, the
+    residual ``data - estimate`` (llckbdm.py:163), the model of the lines kept in each iteration (``multi_fid``, llckbdm.py:177)
+    and the final RMSE (llckbdm.py:192) are all computed there -- nothing of FID length returns to the host."""
     if max_iterations < 1:
         raise ValueError("'max_iterations must be greater than zero")
-    estimate = np.zeros_like(data)
+    if len(m_range) < 2:
+        raise ValueError("size of 'm_range' must be greater than 2.")
+    torch = _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_points = len(data)
+    ms, ls = _resolve_members(n_points, m_range, l, p)
+    need = max(2 * mm + p - 1 for mm in ms)
+    check_finite(data, (need - p + 1) // 2, p)
+    data_dev = to_device_complex(np.asarray(data).ravel(), dev)
+    estimate_dev = torch.zeros_like(data_dev)
     line_lists, silhouettes = [], []
-    t_array, _ = gen_t_freq_arrays(N=len(data), dwell=dwell)
     n_peaks = 0
     thresholds = np.linspace(silhouette_threshold, 0, max_iterations)
     for it in range(max_iterations):
         print(f'Iteration #{it}')
-        res = llc_kbdm(data=data - estimate, dwell=dwell, m_range=m_range, p=p, l=l, q=q)
+        resid_dev = data_dev - estimate_dev
+        if not bool(torch.isfinite(torch.view_as_real(resid_dev[:need])).all().item()):
+            raise ValueError("array must not contain infs or NaNs")
+        res = _llc_kbdm_device(resid_dev, dwell, ms, ls, p, q)
         if len(res.line_list) == 0:
             logging.info('No more peaks can be fitted. Stopping.')
             break
         keep = np.nonzero(res.silhouette > np.percentile(res.silhouette, thresholds[it]))
         line_list = res.line_list[keep]
-        # residual model on the device (reference llckbdm.py:177 calls sig_gen.multi_fid on the host)
-        estimate = estimate + multi_fid_batched_device([line_list], len(data), dwell)[0].cpu().numpy()
+        if len(line_list):
+            estimate_dev += multi_fid_batched_device([line_list], n_points, dwell, device=dev)[0]
         line_lists.append(line_list)
         silhouettes.append(res.silhouette[keep])
         n_peaks += len(line_list)
@@ -105,11 +176,15 @@ def iterative_llc_kbdm(data, dwell, m_range, p=1, l=None, q=0.0, max_iterations=
     if not line_lists:
         return IterativeLlcKbdmResult()
     line_list = np.concatenate(line_lists)
-    rmse = calculate_freq_domain_rmse(data=estimate, params_est=line_list, dwell=dwell)
+    with torch.cuda.device(dev):
+        rows = torch.tensor([len(line_list)], dtype=torch.int32, device=dev)
+        cand = torch.from_numpy(np.ascontiguousarray(line_list.reshape(1, -1, 4))).to(dev) if len(line_list) else \
+            torch.zeros((1, 1, 4), dtype=torch.float64, device=dev)
+        rmse = float(score_rmse_device(estimate_dev, dwell, cand, rows, filter_rows=False).cpu().numpy()[0])
     ragged_ll = np.empty(len(line_lists), dtype=object)
     ragged_sil = np.empty(len(silhouettes), dtype=object)
-    for i, (a, s) in enumerate(zip(line_lists, silhouettes)):
-        ragged_ll[i], ragged_sil[i] = a, s
+    for i, (a, s_) in enumerate(zip(line_lists, silhouettes)):
+        ragged_ll[i], ragged_sil[i] = a, s_
     return IterativeLlcKbdmResult(line_list=line_list, line_lists=ragged_ll, silhouettes=ragged_sil, rmse=rmse)
 
 
@@ -129,38 +204,57 @@ def _inverse_transform_line_lists(transformed_line_lists, dwell):
                             transformed_line_lists[:, 3]))
 
 
+def _library_min_samples(min_samples, n):
+    """The reference's ``hdbscan.HDBSCAN(min_samples=k)`` in the installed clusterer's convention: ``hdbscan`` clips k to n-1 and
+    does not count the point itself; sklearn counts it (k+1)."""
+    k = max(1, min(int(min_samples), n - 1))
+    return k + 1 if _HDBSCAN_COUNTS_SELF else k
+
+
 def _fit_one(features, min_samples):
-    model = _HDBSCAN(min_samples=min_samples)
+    """One library fit with the reference's parameters (llckbdm.py:280-283)."""
+    kw = {"copy": True} if _HDBSCAN_COUNTS_SELF else {}
+    model = _HDBSCAN(min_samples=_library_min_samples(min_samples, len(features)), **kw)
     model.fit(features)
     return np.asarray(model.labels_)
 
 
+def _labels_from_msts(src, dst, w):
+    """Labels of all fits from their spanning trees (int64 [F, n-1] x2, float64 [F, n-1]): the edges are sorted with the
+    clusterer's own call (``np.argsort`` of the weights, sklearn ``_process_mst``) so that equal weights keep its order -- on
+    threads, numpy releases the GIL -- and the trees are condensed and labelled by ``llck_hdbscan_labels`` on native threads."""
+    lib = _native.load()
+    F, ne = w.shape
+    n = ne + 1
+    jobs = CLUSTER_JOBS or (os.cpu_count() or 1)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    if F > 1 and jobs > 1:
+        with ThreadPoolExecutor(max_workers=min(jobs, F)) as pool:
+            order = np.stack(list(pool.map(np.argsort, w)))
+    else:
+        order = np.stack([np.argsort(row) for row in w])
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    src = np.ascontiguousarray(src, dtype=np.int64)
+    dst = np.ascontiguousarray(dst, dtype=np.int64)
+    labels = np.empty((F, n), dtype=np.int32)
+    rc = lib.llck_hdbscan_labels(src.ctypes.data, dst.ctypes.data, w.ctypes.data, order.ctypes.data, n, F, MIN_CLUSTER_SIZE,
+                                 int(jobs), labels.ctypes.data)
+    _native.check_rc(rc, "llck_hdbscan_labels")
+    return [labels[f].astype(np.intp) for f in range(F)]
+
+
 def _labels_from_mst(src, dst, w):
-    """The host half of sklearn.cluster.HDBSCAN.fit after the spanning tree: sort the edges, single-linkage tree, condensed tree,
-    EOM selection (``_process_mst`` + ``tree_to_labels`` with the estimator's defaults)."""
-    from sklearn.cluster._hdbscan._linkage import MST_edge_dtype, make_single_linkage
-    from sklearn.cluster._hdbscan._tree import tree_to_labels
-    mst = np.empty(len(w), dtype=MST_edge_dtype)
-    mst["current_node"], mst["next_node"], mst["distance"] = src, dst, w
-    mst = mst[np.argsort(mst["distance"])]
-    ref = _HDBSCAN()
-    labels, _ = tree_to_labels(make_single_linkage(mst), ref.min_cluster_size, ref.cluster_selection_method,
-                               ref.allow_single_cluster, ref.cluster_selection_epsilon, ref.max_cluster_size)
-    return np.asarray(labels)
+    """One fit (see ``_labels_from_msts``)."""
+    return _labels_from_msts(np.asarray(src)[None, :], np.asarray(dst)[None, :], np.asarray(w, dtype=np.float64)[None, :])[0]
 
 
 def _gpu_fit_supported(features, min_samples_list):
-    """The device spanning trees reproduce sklearn's Euclidean Prim path edge for edge; anything else (the external ``hdbscan``
-    package, non-finite features, sizes outside the kernels' limits) keeps the plain host fits."""
-    if os.environ.get("LLCK_GPU_MST", "1") == "0" or not _HDBSCAN.__module__.startswith("sklearn."):
-        return False
+    """Sizes the device kernels handle (n <= 131072 points, k+1 <= 128 neighbours) and finite features; anything else keeps
+    the plain library fits."""
     n = len(features)
-    if n < 2 or n > 131072 or not min_samples_list or max(min_samples_list) > min(128, n) or min(min_samples_list) < 1:
+    if CLUSTER_BACKEND != "device" or n < 2 or n > 131072 or not min_samples_list or min(min_samples_list) < 1:
         return False
-    try:
-        from sklearn.cluster._hdbscan._linkage import MST_edge_dtype, make_single_linkage  # noqa: F401
-        from sklearn.cluster._hdbscan._tree import tree_to_labels  # noqa: F401
-    except Exception:  # noqa: BLE001
+    if min(max(min_samples_list), n - 1) + 1 > 128:
         return False
     return bool(np.isfinite(features).all())
 
@@ -168,21 +262,18 @@ def _gpu_fit_supported(features, min_samples_list):
 def _fit_all(features, min_samples_list):
     """Labels of one HDBSCAN fit per min_samples value, in order (reference llckbdm.py:104-116 + :280-283).
 
-    With sklearn's HDBSCAN as the clusterer the two O(n^2) stages of every fit -- k-nearest-neighbour core distances and Prim's
-    spanning tree of the mutual-reachability graph -- run on the device for all min_samples values at once
-    (``ensemble.hdbscan_msts_device``, edge lists identical to the host's), and only the O(n log n) tree condensation runs on the
-    host, spread over worker processes.  Otherwise the fits run on the host (in parallel processes when there are enough of them;
-    LLCK_CLUSTER_JOBS overrides the worker count, 1 = serial)."""
+    Device path (default): core distances and Prim's spanning tree of the mutual-reachability graph for all min_samples values at
+    once (``ensemble.hdbscan_msts_device``; edges bit-identical to sklearn's exact Prim), then ``_labels_from_msts``.  Otherwise
+    the library fits run on the host (in parallel processes when there are enough of them)."""
     n_fits = len(min_samples_list)
-    jobs = int(os.environ.get("LLCK_CLUSTER_JOBS", "0")) or min(n_fits, os.cpu_count() or 1)
-    parallel = jobs > 1 and n_fits >= 8 and len(features) >= 4000
+    n = len(features)
     if _gpu_fit_supported(features, min_samples_list):
-        src, dst, w = hdbscan_msts_device(features, min_samples_list)
-        if not parallel:
-            return [_labels_from_mst(src[f], dst[f], w[f]) for f in range(n_fits)]
-        from joblib import Parallel, delayed
-        return Parallel(n_jobs=jobs, prefer="processes")(delayed(_labels_from_mst)(src[f], dst[f], w[f]) for f in range(n_fits))
-    if not parallel:
+        # neighbour counts INCLUDING the point itself (see the module docstring)
+        ks = [min(int(ms), n - 1) + 1 for ms in min_samples_list]
+        src, dst, w = hdbscan_msts_device(features, ks)
+        return _labels_from_msts(src, dst, w)
+    jobs = CLUSTER_JOBS or min(n_fits, os.cpu_count() or 1)
+    if not (jobs > 1 and n_fits >= 8 and n >= 4000):
         return [_fit_one(features, ms) for ms in min_samples_list]
     from joblib import Parallel, delayed
     return Parallel(n_jobs=jobs, prefer="processes")(delayed(_fit_one)(features, ms) for ms in min_samples_list)

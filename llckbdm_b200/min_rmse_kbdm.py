@@ -4,6 +4,7 @@ metrics.py:7-17) runs on the device (``llck_rmse_batched``): fused with the solv
 line lists, one packed launch when they are given by the caller."""
 import logging
 
+import attr
 import numpy as np
 
 from .ensemble import score_candidates
@@ -13,15 +14,14 @@ from .sig_gen import _validate_parameters
 logger = logging.getLogger(__name__)
 
 
+@attr.s
 class MinRmseKbdmResult:
-    __slots__ = ("line_list", "min_rmse", "min_index", "samples", "rmses_list")
-
-    def __init__(self, line_list, min_rmse, min_index, samples, rmses_list):
-        self.line_list = line_list
-        self.min_rmse = min_rmse
-        self.min_index = min_index
-        self.samples = samples
-        self.rmses_list = rmses_list
+    """Same attrs record as reference min_rmse_kbdm.py:12-18."""
+    line_list = attr.ib()
+    min_rmse = attr.ib()
+    min_index = attr.ib()
+    samples = attr.ib()
+    rmses_list = attr.ib()
 
 
 def min_rmse_kbdm(data, dwell, m_range=None, l=None, samples=None):

@@ -211,18 +211,27 @@ def test_gpu_hdbscan_spanning_trees_give_identical_labels(cuda):
     X = np.column_stack([X, np.zeros(len(X))])
     X[7] = X[3]                                    # duplicate points: zero distances
     X[100:110, :3] = np.round(X[100:110, :3], 1)   # coarse grid: exact distance ties
-    ks = [1, 2, 5, 9, 33]
+    from sklearn.cluster import HDBSCAN
+    ks = [1, 2, 5, 9, 33]                          # neighbour counts INCLUDING the point itself (sklearn's min_samples)
     src, dst, w = hdbscan_msts_device(X, ks)
     for f, k in enumerate(ks):
         cd = np.ascontiguousarray(NearestNeighbors(n_neighbors=k, algorithm="kd_tree").fit(X).kneighbors(X, k)[0][:, -1])
         ref = mst_from_data_matrix(np.asarray(X, order="C"), cd, DistanceMetric.get_metric("euclidean"), 1.0)
         assert np.array_equal(src[f], ref["current_node"]) and np.array_equal(dst[f], ref["next_node"])
         assert np.array_equal(w[f], ref["distance"])
-        assert np.array_equal(L._labels_from_mst(src[f], dst[f], w[f]), L._fit_one(X, k))
-    assert L._gpu_fit_supported(X, ks)
+        assert np.array_equal(L._labels_from_mst(src[f], dst[f], w[f]), HDBSCAN(min_samples=k, copy=True).fit(X).labels_)
+    # the reference's hdbscan.HDBSCAN(min_samples=k) does not count the point itself: k+1 in sklearn's convention
+    assert L._gpu_fit_supported(X, list(range(1, 12)))
     got = L._fit_all(X, list(range(1, 12)))
     for k, lab in zip(range(1, 12), got):
+        assert np.array_equal(lab, HDBSCAN(min_samples=k + 1, copy=True).fit(X).labels_), k
         assert np.array_equal(lab, L._fit_one(X, k)), k
+    L.CLUSTER_BACKEND = "host"                     # explicit switch (no environment variable): plain library fits
+    try:
+        assert not L._gpu_fit_supported(X, [1, 2])
+        assert np.array_equal(L._fit_all(X, [3])[0], got[2])
+    finally:
+        L.CLUSTER_BACKEND = "device"
 
 
 def test_llc_kbdm_matches_host_clustering_stage(cuda):
@@ -348,8 +357,9 @@ def test_zgemm_stage_entry_hankel_and_conjt(cuda):
 
 
 def test_full_size_m1024_properties(cuda):
-    """BASELINE size (N=2048, m=l=1024): size-independent properties instead of the (slow) oracle eig:
-    singular values vs LAPACK, generalized-eigen residual of every pole, amplitude identity, signal reconstruction."""
+    """BASELINE size (N=2048, m=l=1024): size-independent properties (the pole-by-pole oracle comparison at this size is
+    tests/test_gpu_configs.py::test_headline_m1024_all_poles_against_oracle): singular values vs LAPACK, generalized-eigen
+    residual of sampled poles, amplitude identity, signal reconstruction."""
     from llckbdm_b200.ensemble import solve_ensemble
     from oracle.kbdm_oracle import brain_sim, hankel_matrices
     c = brain_sim(2048, 1e-3, 0)
@@ -371,21 +381,6 @@ def test_full_size_m1024_properties(cuda):
     assert np.abs(recon - c[:64]).max() < 1e-7 * np.abs(c).max()
     ll = res.line_lists[0]
     assert np.allclose(ll[:, 0], np.abs(D)) and np.allclose(ll[:, 3], np.angle(D))
-
-
-def test_c2_ensemble_shape_subset_parity(cuda):
-    """A slice of config C2 (m in [700,1024], ragged batch) against the oracle on the two smallest members."""
-    from llckbdm_b200.ensemble import solve_ensemble
-    from oracle.kbdm_oracle import brain_sim, compare_members, kbdm_oracle
-    c = brain_sim(2048, 1e-3, 0)
-    ms = [700, 703, 1024, 857]
-    res = solve_ensemble(c, ms, ms, 1, 0.0, DWELL)
-    assert (res.status == 0).all()
-    for k in (0, 1):
-        _, info_o, mu_o, D_o = kbdm_oracle(c, DWELL, m=ms[k], return_mu=True)
-        dmu, dD = compare_members(res.mu[k, :ms[k]], res.D[k, :ms[k]], mu_o, D_o)
-        assert dmu < TOL and dD < TOL, (ms[k], dmu, dD)
-        assert np.allclose(res.sing_vals[k, :ms[k]], info_o.singular_values, rtol=1e-8, atol=1e-12)
 
 
 def test_bidiag_stage_entry(cuda):
@@ -420,17 +415,17 @@ def test_bidiag_stage_entry(cuda):
         assert np.allclose(np.linalg.svd(B, compute_uv=False), s_ref, rtol=1e-9, atol=1e-12 * s_ref[0])
 
 
-@pytest.mark.parametrize("svd_mode", ["d", "b", "j"])
-def test_both_svd_paths_tiny_and_ragged(cuda, svd_mode, monkeypatch):
-    """Tiny and ragged members (m = 1..65, l < m, p > 1, q > 0) through all SVD back ends: 'd' = bidiagonalisation +
-    divide and conquer (default), 'b' = bidiagonalisation + real Jacobi, 'j' = complex Jacobi on U directly."""
-    monkeypatch.setenv("LLCK_SVD", svd_mode)
+@pytest.mark.parametrize("svd_mode", ["dc", "jacobi"])
+def test_both_svd_paths_tiny_and_ragged(cuda, svd_mode):
+    """Tiny and ragged members (m = 1..65, l < m, p > 1, q > 0) through both SVD back ends of the bidiagonal, selected by the
+    explicit llck_options struct: divide and conquer (default) and the real block Jacobi (what rank-deficient members fall back to)."""
+    from llckbdm_b200 import _native
     from llckbdm_b200.ensemble import solve_ensemble
-    from llckbdm_b200.kbdm import kbdm
-    from oracle.kbdm_oracle import brain_sim, compare_members, kbdm_oracle, mu_from_line_list
+    from oracle.kbdm_oracle import brain_sim, compare_members, kbdm_oracle
+    opts = _native.Options(svd_mode=_native.SVD_JACOBI if svd_mode == "jacobi" else _native.SVD_DC)
     c = brain_sim(2048, 1e-3, 7)
     ms = [1, 2, 3, 5, 31, 32, 34, 65]
-    res = solve_ensemble(c, ms, ms, 1, 0.0, DWELL)
+    res = solve_ensemble(c, ms, ms, 1, 0.0, DWELL, options=opts)
     assert (res.status == 0).all()
     for k, m in enumerate(ms):
         _, info, mu, D = kbdm_oracle(c, DWELL, m=m, return_mu=True)
@@ -438,9 +433,10 @@ def test_both_svd_paths_tiny_and_ragged(cuda, svd_mode, monkeypatch):
         assert dmu < TOL and dD < TOL, (m, dmu, dD)
         assert np.allclose(res.sing_vals[k, :m], info.singular_values, rtol=1e-8, atol=1e-12)
     for (m, l, p, q) in [(64, 1, 1, 0.0), (40, 2, 3, 0.0), (100, 7, 1, 1e-2), (33, 33, 4, 0.0)]:
-        ll, _ = kbdm(c, DWELL, m=m, l=l, p=p, q=q)
+        r = solve_ensemble(c, [m], [l], p, q, DWELL, options=opts)
+        assert r.status[0] == 0
         _, _, mu, D = kbdm_oracle(c, DWELL, m=m, l=l, p=p, q=q, return_mu=True)
-        dmu, dD = compare_members(mu_from_line_list(ll, DWELL), ll[:, 0] * np.exp(1j * ll[:, 3]), mu, D)
+        dmu, dD = compare_members(r.mu[0, :l], r.D[0, :l], mu, D)
         assert dmu < TOL and dD < TOL, (m, l, p, q, dmu, dD)
 
 

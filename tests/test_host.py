@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from llckbdm_b200 import _native
-from llckbdm_b200.ensemble import flatten_signals, flops_per_solve, lpt_shards
+from llckbdm_b200.ensemble import flatten_signals, flops_per_solve, lpt_shards, plan_chunks
 from llckbdm_b200.kbdm import raise_for_status, resolve_m_l
 from llckbdm_b200.sampling import filter_samples
 
@@ -16,11 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(native_lib):
     header = open(os.path.join(ROOT, "include", "llck.h")).read()
-    declared = set(re.findall(r"\b(llck_[a-z_0-9]+)\s*\(", header))
+    declared = set(re.findall(r"^(?:int|size_t)\s+(llck_[a-z_0-9]+)\s*\(", header, flags=re.M))
     assert declared == set(_native.SYMBOLS)
     for sym in declared:
         assert getattr(native_lib, sym) is not None
-    assert native_lib.llck_version() == 100
+    assert native_lib.llck_version() == 200
 
 
 def test_pure_abi_functions(native_lib):
@@ -38,13 +38,32 @@ def test_pure_abi_functions(native_lib):
 
 
 def test_bad_arguments_are_rejected_without_a_gpu(native_lib):
-    m = (ctypes.c_int32 * 1)(8)
-    l = (ctypes.c_int32 * 1)(9)          # l > m
     off = (ctypes.c_int64 * 1)(0)
     dummy = ctypes.c_void_p(16)
-    rc = native_lib.llck_kbdm_batched(dummy, off, m, l, 1, 0.0, 5e-4, 1, dummy, 64, None, None, 0, dummy, 16, dummy, dummy,
-                                      dummy, 1 << 30, 0, None, None)
-    assert rc == 1
+
+    def call(m, l, n, p=1, opts=None, ws=1 << 40):
+        return native_lib.llck_kbdm_batched(dummy, off, (ctypes.c_int64 * 1)(n), (ctypes.c_int32 * 1)(m), (ctypes.c_int32 * 1)(l),
+                                            p, 0.0, 5e-4, 1, dummy, 4 * l, None, None, 0, dummy, m, dummy, dummy,
+                                            dummy, ws, 0, opts, None, None)
+
+    assert call(8, 9, 64) == _native.E_BADARG                # l > m
+    assert call(8, 8, 14) == _native.E_SHORT_SIGNAL          # needs 2m + p - 1 = 16 points
+    assert call(8, 8, 16, p=2) == _native.E_SHORT_SIGNAL     # p = 2 needs 17
+    assert call(2100, 2100, 5000) == _native.E_TOO_LARGE     # m above LLCK_M_MAX
+    assert call(64, 64, 128, ws=1024) == _native.E_WORKSPACE
+    bad = _native.Options(svd_mode=7)
+    assert call(8, 8, 64, opts=ctypes.byref(bad)) == _native.E_BADARG
+    bad = _native.Options(cluster_size=3)
+    assert call(8, 8, 64, opts=ctypes.byref(bad)) == _native.E_BADARG
+    with pytest.raises(ValueError, match="shorter than the 2m"):
+        _native.check_rc(_native.E_SHORT_SIGNAL, "llck_kbdm_batched")
+
+
+def test_library_reads_no_environment():
+    """The C-ABI library has no hidden switches: no getenv anywhere in the CUDA sources (tuning knobs are llck_options fields)."""
+    csrc = os.path.join(ROOT, "llckbdm_b200", "csrc")
+    for f in os.listdir(csrc):
+        assert "getenv" not in open(os.path.join(csrc, f)).read(), f
 
 
 def test_product_path_fails_loudly_without_cuda():
@@ -113,12 +132,21 @@ def test_lpt_shards_balance_and_cover():
         assert max(loads) / (sum(loads) / world) < 1.05
 
 
+def test_plan_chunks_whole_waves():
+    assert plan_chunks(100, 780) == 100                      # fits: one chunk
+    assert plan_chunks(1184, 780) == 592                     # two equal chunks of 4 waves, not 780 + 404
+    assert plan_chunks(10000, 780) % 148 == 0 and plan_chunks(10000, 780) <= 780
+    assert plan_chunks(65536, 3000) % 148 == 0
+    assert plan_chunks(300, 100) == 100                      # memory cap below one wave
+    assert plan_chunks(7, 3) == 3
+
+
 def test_flatten_signals():
     a = np.arange(4) + 0j
-    flat, off = flatten_signals(a, 3)
-    assert flat.shape == (4,) and list(off) == [0, 0, 0]
-    flat, off = flatten_signals([a, a[:2], a], 3)
-    assert flat.shape == (10,) and list(off) == [0, 4, 6]
+    flat, off, lens = flatten_signals(a, 3)
+    assert flat.shape == (4,) and list(off) == [0, 0, 0] and list(lens) == [4, 4, 4]
+    flat, off, lens = flatten_signals([a, a[:2], a], 3)
+    assert flat.shape == (10,) and list(off) == [0, 4, 6] and list(lens) == [4, 2, 4]
     with pytest.raises(ValueError):
         flatten_signals([a], 2)
 
@@ -140,38 +168,44 @@ def test_sig_gen_and_metrics():
     assert abs(f[np.argmax(peak.real)] - 100.0) < 1.0
 
 
-def test_labels_from_mst_reproduces_hdbscan_fit():
-    """Host half of the device-accelerated HDBSCAN fits: feeding the clusterer's OWN spanning tree (sklearn's Prim) through
-    llckbdm._labels_from_mst must reproduce HDBSCAN(min_samples=k).fit(X).labels_ exactly (the GPU test checks that the device
-    spanning trees equal sklearn's edge for edge)."""
+def _sklearn_mst(X, k_self):
+    """sklearn's own exact spanning tree of the mutual-reachability graph (core distance = k_self-th neighbour incl. the point)."""
     from sklearn.cluster._hdbscan._linkage import mst_from_data_matrix
     from sklearn.metrics import DistanceMetric
     from sklearn.neighbors import NearestNeighbors
+    cd = np.ascontiguousarray(NearestNeighbors(n_neighbors=k_self, algorithm="kd_tree").fit(X).kneighbors(X, k_self)[0][:, -1])
+    return mst_from_data_matrix(np.asarray(X, order="C"), cd, DistanceMetric.get_metric("euclidean"), 1.0)
+
+
+def test_native_labels_from_mst_reproduce_hdbscan_fit():
+    """Host half of the device-accelerated HDBSCAN fits (llck_hdbscan_labels: dendrogram, condensed tree, EOM, labelling on native
+    threads): feeding the clusterer's OWN spanning tree (sklearn's exact Prim) through it must reproduce
+    sklearn.cluster.HDBSCAN(min_samples=k+1).fit(X).labels_ label for label -- k+1 because the reference's hdbscan package does
+    not count the point itself (the GPU test checks that the device spanning trees equal sklearn's edge for edge).
+    Inputs include tight clusters, duplicate points (zero distances -> infinite lambdas) and exact distance ties."""
+    from sklearn.cluster import HDBSCAN
     from llckbdm_b200 import llckbdm as L
     rng = np.random.default_rng(1)
     cent = rng.uniform(-1, 1, (8, 3))
     X = np.concatenate([np.repeat(cent, 10, axis=0) + 1e-5 * rng.standard_normal((80, 3)), rng.uniform(-1, 1, (300, 3))])
     X = np.column_stack([X, np.zeros(len(X))])
-    for k in (1, 4, 11):
-        cd = np.ascontiguousarray(NearestNeighbors(n_neighbors=k, algorithm="kd_tree").fit(X).kneighbors(X, k)[0][:, -1])
-        mst = mst_from_data_matrix(np.asarray(X, order="C"), cd, DistanceMetric.get_metric("euclidean"), 1.0)
-        got = L._labels_from_mst(mst["current_node"], mst["next_node"], mst["distance"])
-        assert np.array_equal(got, L._fit_one(X, k))
-
-
-def test_cluster_grouping_matches_reference_semantics(monkeypatch):
-    """_results_from_labelings (one stable sort per labeling) == the reference's per-cluster np.nonzero / np.average loops
-    (llckbdm.py:297-313, 324-353); the device silhouettes are replaced by a fixed array here."""
-    from llckbdm_b200 import llckbdm as L
-    rng = np.random.default_rng(0)
-    n = 3000
-    samples = np.column_stack([rng.random(n) + 0.1, rng.random(n) * 0.1 + 0.01, rng.uniform(-500, 500, n), rng.uniform(-1, 1, n)])
-    labels = rng.integers(-1, 25, n)
-    sil = rng.uniform(-1, 1, n)
-    monkeypatch.setattr(L, "silhouette_samples_device", lambda feats, labelings: np.array([sil for _ in labelings]))
-    res = L._results_from_labelings(samples, samples, [labels, np.full(n, -1)])
-    assert len(res) == 1 and res[0].num_clusters == 25
-    clusters = [np.nonzero(labels == k) for k in range(25)]
-    assert all(np.array_equal(a[0], b[0]) for a, b in zip(res[0].clustered, clusters))
-    assert np.allclose(res[0].summarized_line_list, L._summarize_clusters(samples, clusters), rtol=1e-13, atol=0)
-    assert np.allclose(res[0].clustered_silhouettes, [np.average(sil[c]) for c in clusters], rtol=1e-13, atol=1e-16)
+    X2 = X.copy()
+    X2[5] = X2[3]; X2[6] = X2[3]; X2[90:96] = X2[90]            # duplicates
+    X2[100:140, :3] = np.round(X2[100:140, :3], 1)              # coarse grid: exact ties
+    X3 = np.column_stack([rng.integers(0, 6, (500, 3)).astype(float), np.zeros(500)])   # integer lattice: massive ties + duplicates
+    for Xc in (X, X2, X3):
+        ks = (1, 2, 4, 11, 30)
+        msts = [_sklearn_mst(Xc, k + 1) for k in ks]
+        src = np.stack([t["current_node"] for t in msts]); dst = np.stack([t["next_node"] for t in msts])
+        w = np.stack([t["distance"] for t in msts])
+        got = L._labels_from_msts(src, dst, w)
+        for k, g in zip(ks, got):
+            want = HDBSCAN(min_samples=k + 1, copy=True).fit(Xc).labels_
+            assert np.array_equal(g, want), k
+            assert np.array_equal(g, L._fit_one(Xc, k)), k       # the library path uses the same convention
+    # one fit through the single-tree helper; clipping of k to n-1
+    t = _sklearn_mst(X, 5)
+    assert np.array_equal(L._labels_from_mst(t["current_node"], t["next_node"], t["distance"]), HDBSCAN(min_samples=5, copy=True).fit(X).labels_)
+    tiny = X[:7]
+    assert np.array_equal(L._fit_one(tiny, 50), HDBSCAN(min_samples=7, copy=True).fit(tiny).labels_)
+    assert L._library_min_samples(50, 7) == 7 and L._library_min_samples(1, 100) == 2

@@ -3,9 +3,9 @@
 # usage: bash tools/ncu_pass.sh TAG [full]
 set -x
 TAG=${1:-r01c}
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-c2"
+CMD="python bench.py --steps 1 --warmup 1 --members 148 --e2e-steps 1 --no-cpu-baseline --no-configs --no-weak"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "list rc=$?"
 if [ "$2" = "full" ]; then
   cap() {   # name regex skip
