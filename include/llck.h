@@ -56,6 +56,9 @@ extern "C" {
 #define LLCK_FLAG_TIMING 2           /* diagnostic: record CUDA events between stages, WAIT for the stream, return stage durations (us)
                                         in info[4..12] and the maximum number of QR sweeps in info[1] */
 
+#define LLCK_FLAG_NO_GRAPH 4         /* do not use a CUDA graph WHILE node for the Jacobi sweeps: enqueue all of them (their CTAs exit
+                                        at once for converged members); for callers that are themselves capturing the stream */
+
 /* SVD back end for the real bidiagonal (llck_options.svd_mode) */
 #define LLCK_SVD_DC 0                /* divide and conquer; members it flags as numerically rank deficient fall back to Jacobi (default) */
 #define LLCK_SVD_JACOBI 1            /* block one-sided Jacobi for every member */
@@ -100,7 +103,8 @@ size_t llck_debug_offset(int batch, int ld, int which);
  *   status     [dev]  int32   [batch]              LLCK_STATUS_*
  *   opts       [host] llck_options (optional, NULL = defaults)
  *   info       [host] int32   [16] (optional)      [2]=ld, [3]=Jacobi column blocks of the largest member, [13]=kernels enqueued by
- *                                                  this call (counted at the launch sites), [14]=Jacobi rounds enqueued; with
+ *                                                  this call (counted at the launch sites; a graph launch counts once),
+ *                                                  [14]=1 if the Jacobi sweeps ran as a device-side WHILE graph node; with
  *                                                  LLCK_FLAG_TIMING also [1]=max QR multishift sweeps and [4..12]=stage durations in us
  *                                                  (init + bidiagonalisation, SVD of the bidiagonal, back-multiplication, T1+Ured,
  *                                                  hessenberg, hqr, trevc, P+B+W, epilogue)
@@ -108,8 +112,10 @@ size_t llck_debug_offset(int batch, int ld, int which);
  * divide-and-conquer SVD of the bidiagonal) + panel / bookkeeping vectors.  Batches of <= 74 members run the one-CTA-per-member
  * kernels as thread-block clusters of 2/4/8 CTAs per member.
  * Asynchronous: returns once the launch sequence is enqueued on `stream` (LLCK_FLAG_TIMING makes it wait).  The Jacobi fallback
- * is enqueued unconditionally -- llck_options.jacobi_max_sweeps sweeps whose CTAs exit at once for members the divide-and-conquer
- * SVD solved -- so that no decision needs a device-to-host read-back.
+ * for members the divide-and-conquer SVD flags is ONE CUDA-graph launch whose conditional WHILE node repeats the sweep on the
+ * device until every member has converged (at most llck_options.jacobi_max_sweeps times; zero times when no member was flagged),
+ * so no decision needs a device-to-host read-back.  (A small graph is built and released inside the call: host-side objects
+ * only, no device memory.)
  */
 int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int64_t* sig_len, const int32_t* m, const int32_t* l,
                       int32_t p, double q, double dwell, int32_t batch,

@@ -30,6 +30,7 @@ SYMBOLS = (
 
 FLAG_DEBUG_KEEP = 1
 FLAG_TIMING = 2
+FLAG_NO_GRAPH = 4
 
 E_BADARG = 1
 E_WORKSPACE = 2

@@ -70,6 +70,23 @@ __global__ void fallback_to_done_kernel(const int* fallback, int* done, int batc
     if (b < batch) done[b] = fallback[b] ? 0 : 1;
 }
 
+// loop condition of the Jacobi sweeps (CUDA graph WHILE node): another sweep iff some member is not converged and sweeps are left.
+// First node of the graph (decrement = 0) and last node of every sweep (decrement = 1).
+__global__ void jacobi_cond_kernel(cudaGraphConditionalHandle handle, const int* done, int batch, int* sweeps_left, int decrement) {
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) mine |= !done[b];
+    if (mine) any = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int left = *sweeps_left - decrement;
+        *sweeps_left = left;
+        cudaGraphSetConditional(handle, (any && left > 0) ? 1u : 0u);
+    }
+}
+
 // per-call device state: convergence flags, outputs that are accumulated with atomics
 __global__ void meta_zero_kernel(int* done, unsigned long long* sweep_off, int* status, int* n_valid, int* hqr_sweeps, int batch) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,7 +96,7 @@ __global__ void meta_zero_kernel(int* done, unsigned long long* sweep_off, int* 
 
 // ---- workspace layout -----------------------------------------------------------------------------
 struct WsLayout {
-    size_t mv, lv, nbv, done, hqr_sweeps, perm, sig_off, sweep_off, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, bdcvec, fallback, ypart, mats, total;
+    size_t mv, lv, nbv, done, scalars, hqr_sweeps, perm, sig_off, sweep_off, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, bdcvec, fallback, ypart, mats, total;
     int nmats;
 };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -90,6 +107,7 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
     L.lv = o; o = al256(o + sizeof(int) * batch);
     L.nbv = o; o = al256(o + sizeof(int) * batch);
     L.done = o; o = al256(o + sizeof(int) * batch);
+    L.scalars = o; o = al256(o + 256);
     L.hqr_sweeps = o; o = al256(o + sizeof(int) * batch);
     L.perm = o; o = al256(o + sizeof(int) * (size_t)batch * ld);
     L.sig_off = o; o = al256(o + sizeof(long long) * batch);
@@ -228,6 +246,74 @@ static int bidiag_driver(cplx* A, cplx* Q, cplx* P, long long stride, int ld, co
         }
     }
     return 0;
+}
+
+// One Jacobi sweep on `st` (all rounds + the convergence bookkeeping); CTAs of converged members exit at once.
+static cudaError_t enqueue_jacobi_sweep(RJacobiParams rp, int nbmax, int batch, unsigned long long* d_swoff, int* d_done, double conv2, cudaStream_t st) {
+    for (int r = 0; r < nbmax - 1; ++r) {
+        rp.round = r;
+        dim3 gA(nbmax / 2, batch), gA2(nbmax / 2, batch, 2);
+        rjacobi_gram_kernel<<<gA, 256, RJ_GRAM_SMEM, st>>>(rp);
+        rjacobi_eig_kernel<<<gA, RJE_THREADS, RJE_SMEM, st>>>(rp);
+        rjacobi_update_kernel<<<gA2, 256, RJ_UPD_SMEM, st>>>(rp);
+    }
+    jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, batch, conv2);
+    return cudaGetLastError();
+}
+
+// The Jacobi iteration as ONE graph launch: a device-side WHILE node (CUDA graph conditional node) repeats the sweep while some
+// member is unconverged and sweeps are left -- no host read-back, and nothing at all runs when the divide-and-conquer SVD solved
+// every member.  Returns cudaErrorNotSupported-like errors to the caller, which then enqueues the sweeps unconditionally.
+static cudaError_t launch_jacobi_while_graph(const RJacobiParams& rp, int nbmax, int batch, int max_sweeps, unsigned long long* d_swoff,
+                                             int* d_done, double conv2, int* d_sweeps_left, cudaStream_t st) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t cap = nullptr;
+    cudaError_t e = cudaSuccess;
+    bool capturing = false;
+    do {
+        if ((e = cudaMemcpyAsync(d_sweeps_left, &max_sweeps, sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((e = cudaGraphCreate(&graph, 0)) != cudaSuccess) break;
+        cudaGraphConditionalHandle handle;
+        if ((e = cudaGraphConditionalHandleCreate(&handle, graph, 0, 0)) != cudaSuccess) break;
+        cudaGraphNode_t first = nullptr, loop = nullptr;
+        {
+            int dec = 0;
+            const int* done_c = d_done;
+            void* args[] = {&handle, &done_c, &batch, &d_sweeps_left, &dec};
+            cudaKernelNodeParams kp = {};
+            kp.func = (void*)jacobi_cond_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(256); kp.sharedMemBytes = 0; kp.kernelParams = args;
+            if ((e = cudaGraphAddKernelNode(&first, graph, nullptr, 0, &kp)) != cudaSuccess) break;
+        }
+        cudaGraphNodeParams cp = {};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        if ((e = cudaGraphAddNode(&loop, graph, &first, 1, &cp)) != cudaSuccess) break;
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        if ((e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed)) != cudaSuccess) break;
+        capturing = true;
+        e = enqueue_jacobi_sweep(rp, nbmax, batch, d_swoff, d_done, conv2, cap);
+        if (e == cudaSuccess) {
+            jacobi_cond_kernel<<<1, 256, 0, cap>>>(handle, d_done, batch, d_sweeps_left, 1);
+            e = cudaGetLastError();
+        }
+        cudaGraph_t ended = nullptr;
+        cudaError_t e2 = cudaStreamEndCapture(cap, &ended);
+        capturing = false;
+        if (e == cudaSuccess) e = e2;
+        if (e != cudaSuccess) break;
+        if ((e = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess) break;
+        e = cudaGraphLaunch(exec, st);
+    } while (0);
+    if (capturing) { cudaGraph_t ended = nullptr; cudaStreamEndCapture(cap, &ended); }
+    if (exec) cudaGraphExecDestroy(exec);        // an executable graph in flight is released when it completes
+    if (graph) cudaGraphDestroy(graph);
+    if (cap) cudaStreamDestroy(cap);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    return e;
 }
 
 extern "C" {
@@ -467,6 +553,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
     if (dbg) { bX = mat(0); bRs = mat(2); bLt = mat(3); bT1 = mat(4); bH = mat(8); bZ = mat(9); bXev = mat(10); bP = mat(11); bB = mat(12); bW = mat(13); }
     else     { bX = mat(0); bRs = mat(2); bLt = mat(3); bT1 = mat(0); bH = mat(1); bZ = mat(3); bXev = mat(0); bP = mat(4); bB = mat(5); bW = mat(0); }
     llck_launch_count = 0;
+    int jacobi_graph = 0;
 
     // ---- metadata: per-member sizes and FID offsets go to the device through ONE staged copy; the call never waits for the stream ----
     int nbmax = 2;
@@ -563,18 +650,19 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
         rp.pairs_max = ((ld / J_B) + 1) / 2 + 1;
         // a member is converged when no pair exceeded 1e-6 (scaled) during a sweep: that sweep leaves <= ~1e-12
         const double conv = o.jacobi_conv > 0.0 ? o.jacobi_conv : 1e-6;
-        for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-            for (int r = 0; r < nbmax - 1; ++r) {
-                rp.round = r;
-                dim3 gA(nbmax / 2, batch), gA2(nbmax / 2, batch, 2);
-                rjacobi_gram_kernel<<<gA, 256, RJ_GRAM_SMEM, st>>>(rp);
-                rjacobi_eig_kernel<<<gA, RJE_THREADS, RJE_SMEM, st>>>(rp);
-                rjacobi_update_kernel<<<gA2, 256, RJ_UPD_SMEM, st>>>(rp);
-                llck_launch_count += 3;
+        // device-side loop: one graph launch whose WHILE node repeats the sweep until every member has converged (or max_sweeps)
+        int* d_sweeps_left = (int*)(ws + L.scalars);
+        bool looped = false;
+        if (!(flags & LLCK_FLAG_NO_GRAPH)) {
+            looped = launch_jacobi_while_graph(rp, nbmax, batch, max_sweeps, d_swoff, d_done, conv * conv, d_sweeps_left, st) == cudaSuccess;
+            if (looped) { LLCK_LAUNCHED(); jacobi_graph = 1; }
+        }
+        if (!looped) {
+            // without conditional graph nodes: every sweep is enqueued; the CTAs of converged members exit at once
+            for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+                CK(enqueue_jacobi_sweep(rp, nbmax, batch, d_swoff, d_done, conv * conv, st));
+                llck_launch_count += 3 * (nbmax - 1) + 1;
             }
-            jacobi_sweep_end_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_swoff, d_done, batch, conv * conv);
-            LLCK_LAUNCHED();
-            CK(cudaGetLastError());
         }
         mark_unconverged_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_done, status, batch);
         LLCK_LAUNCHED();
@@ -786,7 +874,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
         for (int i = 0; i < 16; ++i) info[i] = 0;
         info[2] = ld; info[3] = nbmax;
         info[13] = llck_launch_count;                 // kernels enqueued by this call, counted at the launch sites
-        info[14] = max_sweeps * (nbmax - 1);          // Jacobi rounds enqueued (their CTAs exit at once for members the D&C solved)
+        info[14] = jacobi_graph;                      // 1: the Jacobi sweeps ran as a device-side WHILE graph node, 0: enqueued unconditionally
     }
     if (timing) {
         // diagnostic mode: the only path that waits for the stream.  info[1] = max QR sweeps over the batch,

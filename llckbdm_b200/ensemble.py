@@ -338,7 +338,7 @@ def to_device_complex(flat, dev):
     return torch.from_numpy(np.ascontiguousarray(flat, dtype=np.complex128).view(np.float64)).to(dev).view(torch.complex128)
 
 
-def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None, score_rmse=False, options=None):
+def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None, score_rmse=False, options=None, flags=0):
     """Solve an ensemble given HOST inputs; returns an ``EnsembleResult`` of host arrays.
 
     signals: either one 1-D complex array shared by all members, or a list of 1-D complex arrays (one per member).
@@ -367,7 +367,7 @@ def solve_ensemble(signals, m, l, p, q, dwell, device=None, chunk=None, score_rm
         out_st = np.zeros(M, dtype=np.int32)
         out_rm = np.full(M, np.inf) if score_rmse else None
         infos = []
-        for idx, r in solve_chunks(sig_dev, offsets, lens, m, l, p, q, dwell, chunk=chunk, options=options):
+        for idx, r in solve_chunks(sig_dev, offsets, lens, m, l, p, q, dwell, chunk=chunk, options=options, flags=flags):
             lm, mm = r["line_lists"].shape[1], r["sing_vals"].shape[1]
             out_ll[idx, :lm] = r["line_lists"].cpu().numpy()
             out_mu[idx, :lm] = r["mu"].cpu().numpy()
