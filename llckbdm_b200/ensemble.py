@@ -65,6 +65,10 @@ def max_chunk(ld, device=None, reserve_frac=0.8, flags=0):
     free, _total = torch.cuda.mem_get_info(device)
     # blocks torch's caching allocator holds but has not handed out (e.g. the workspace of the previous call) are reusable
     free += max(0, torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device))
+    dev_index = torch.cuda.current_device() if device is None or torch.device(device).index is None else torch.device(device).index
+    cached = _WORKSPACES.get(("cuda", dev_index))
+    if cached is not None:
+        free += cached.numel()                       # the kept workspace is what the next call runs in
     lib = _native.load()
     per = lib.llck_workspace_bytes(1, ld, flags)
     return max(1, int(free * reserve_frac // per))
@@ -94,8 +98,7 @@ def sm_count(device=None):
 
 def solve_chunks(sig_dev, offsets, lens, m, l, p, q, dwell, chunk=None, want_mu=True, flags=0, options=None, order=None):
     """Generator over cost-sorted chunks of an ensemble whose FIDs are already on the device: yields (idx, result) with ``idx`` the
-    member indices of the chunk and ``result`` the dict of ``solve_device`` (device tensors, valid until the next iteration: the
-    workspace is reused).  ``chunk=None`` sizes the chunks to the free HBM, rounded to whole waves (``plan_chunks``)."""
+    member indices of the chunk and ``result`` the dict of ``solve_device`` (device tensors; all chunks run in the cached workspace).  ``chunk=None`` sizes the chunks to the free HBM, rounded to whole waves (``plan_chunks``)."""
     torch = _require_cuda()
     lib = _native.load()
     m = np.asarray(m, dtype=np.int32)
@@ -110,13 +113,37 @@ def solve_chunks(sig_dev, offsets, lens, m, l, p, q, dwell, chunk=None, want_mu=
     if order is None:
         # cost-sorted chunks keep similar sizes together (less padding work inside a launch); one chunk keeps the caller's order
         order = np.arange(M) if chunk >= M else np.argsort(-(m.astype(np.int64) * 4096 + l), kind="stable")
-    ws = None
     for c0 in range(0, M, chunk):
         idx = order[c0:c0 + chunk]
-        r = solve_device(sig_dev, offsets[idx], m[idx], l[idx], p, q, dwell, flags=flags, workspace=ws, want_mu=want_mu,
-                         sig_len=lens[idx], options=options)
-        ws = r["workspace"]
-        yield idx, r
+        yield idx, solve_device(sig_dev, offsets[idx], m[idx], l[idx], p, q, dwell, flags=flags, want_mu=want_mu,
+                                sig_len=lens[idx], options=options)
+
+
+_WORKSPACES = {}
+
+
+def get_workspace(nbytes, dev):
+    """The per-device solver workspace, grown on demand and kept between calls (the workspace of a full chunk is most of the HBM:
+    handing it back to the caching allocator after every call fragments it).  ``release_workspace`` frees it."""
+    torch = _require_cuda()
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _WORKSPACES.pop(key, None)
+        del ws
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def release_workspace(dev=None):
+    """Drop the cached solver workspace of ``dev`` (all devices if None)."""
+    if dev is None:
+        _WORKSPACES.clear()
+        return
+    torch = _require_cuda()
+    dev = torch.device(dev)
+    _WORKSPACES.pop((dev.type, dev.index if dev.index is not None else torch.cuda.current_device()), None)
 
 
 def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=None, stream=None, want_mu=True,
@@ -126,7 +153,8 @@ def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=
     signals_dev: torch complex128 CUDA tensor (flat); sig_offset/m/l: host int sequences (one per member);
     sig_len: points of each member's FID (default: everything from its offset to the end of ``signals_dev``);
     options: ``_native.Options`` (explicit tuning knobs) or None.
-    Returns dict of torch CUDA tensors (line_lists, mu, D, sing_vals, n_valid, status) + info list + workspace.
+    workspace: caller-owned uint8 CUDA tensor of at least llck_workspace_bytes; default: the cached per-device workspace.
+    Returns dict of torch CUDA tensors (line_lists, mu, D, sing_vals, n_valid, status) + info list.
     """
     torch = _require_cuda()
     lib = _native.load()
@@ -145,11 +173,12 @@ def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=
     ld = lib.llck_leading_dim(mmax)
     need = lib.llck_workspace_bytes(batch, ld, flags)
     if workspace is None or workspace.numel() < need:
-        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-    line_lists = torch.empty((batch, lmax, 4), dtype=torch.float64, device=dev)
-    mu = torch.empty((batch, lmax), dtype=torch.complex128, device=dev) if want_mu else None
-    D = torch.empty((batch, lmax), dtype=torch.complex128, device=dev) if want_mu else None
-    sv = torch.empty((batch, mmax), dtype=torch.float64, device=dev)
+        workspace = get_workspace(need, dev)
+    # zero-filled: rows beyond a member's own l (m) are padding of the fixed-stride buffers
+    line_lists = torch.zeros((batch, lmax, 4), dtype=torch.float64, device=dev)
+    mu = torch.zeros((batch, lmax), dtype=torch.complex128, device=dev) if want_mu else None
+    D = torch.zeros((batch, lmax), dtype=torch.complex128, device=dev) if want_mu else None
+    sv = torch.zeros((batch, mmax), dtype=torch.float64, device=dev)
     n_valid = torch.empty(batch, dtype=torch.int32, device=dev)
     status = torch.empty(batch, dtype=torch.int32, device=dev)
     info = (ctypes.c_int32 * 16)()
@@ -166,8 +195,7 @@ def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=
         workspace.data_ptr(), need, int(flags), ctypes.byref(options) if options is not None else None,
         st.cuda_stream, info)
     _native.check_rc(rc, "llck_kbdm_batched")
-    return dict(line_lists=line_lists, mu=mu, D=D, sing_vals=sv, n_valid=n_valid, status=status,
-                info=list(info), workspace=workspace, ld=ld)
+    return dict(line_lists=line_lists, mu=mu, D=D, sing_vals=sv, n_valid=n_valid, status=status, info=list(info), ld=ld)
 
 
 def score_rmse_device(data_dev, dwell, line_lists_dev, n_rows_dev, filter_rows=True, amplitude_tol=1e-6, stream=None):

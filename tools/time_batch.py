@@ -11,16 +11,14 @@ sigs = [brain_sim(N, 1e-3, seed=i) for i in range(batch)]
 flat, offs, lens = ensemble.flatten_signals(sigs, batch)
 dev = torch.device("cuda:0")
 sig_dev = torch.from_numpy(flat.view(np.float64)).to(dev).view(torch.complex128)
-ws = None
 names = ["init+bidiag", "svd_bidiagonal", "backmult", "T1+Ured", "hessenberg", "hqr", "trevc", "P+B+W", "epilogue"]
 for r in range(reps):
     torch.cuda.synchronize(); t0 = time.time()
     prof = torch.zeros((batch, 10), dtype=torch.int64, device=dev)
     opts = _native.Options(hqr_profile=prof.data_ptr())
-    out = ensemble.solve_device(sig_dev, offs, [m] * batch, [m] * batch, 1, 0.0, 5e-4, flags=_native.FLAG_TIMING, workspace=ws, sig_len=lens,
+    out = ensemble.solve_device(sig_dev, offs, [m] * batch, [m] * batch, 1, 0.0, 5e-4, flags=_native.FLAG_TIMING, sig_len=lens,
                                 options=opts)
     torch.cuda.synchronize(); dt = time.time() - t0
-    ws = out["workspace"]
     info = out["info"]
     st = out["status"].cpu().numpy()
     print(f"m={m} batch={batch} wall={dt:.3f}s solves/s={batch/dt:.2f} launches={info[13]} max_qr_sweeps={info[1]} bad_status={(st!=0).sum()}")
