@@ -360,19 +360,17 @@ def run_native(args):
         wb = min(148, M)
         w_dev = my_dev[:wb * N] if len(mine) >= wb else sig_host[:wb].to(dev).reshape(-1)
         w_off = np.arange(wb, dtype=np.int64) * N
-        r = None
         for _ in range(2):
-            r = ensemble.solve_device(w_dev, w_off, [m] * wb, [m] * wb, 1, 0.0, DWELL, sig_len=np.full(wb, N), want_mu=False)
-                barrier()
+            ensemble.solve_device(w_dev, w_off, [m] * wb, [m] * wb, 1, 0.0, DWELL, sig_len=np.full(wb, N), want_mu=False)
+        barrier()
         e0.record()
         for _ in range(3):
-            r = ensemble.solve_device(w_dev, w_off, [m] * wb, [m] * wb, 1, 0.0, DWELL, sig_len=np.full(wb, N), want_mu=False)
+            ensemble.solve_device(w_dev, w_off, [m] * wb, [m] * wb, 1, 0.0, DWELL, sig_len=np.full(wb, N), want_mu=False)
         e1.record()
         barrier()
         wms = max_over_ranks(e0.elapsed_time(e1)) / 3
         out["weak_148_per_gpu"] = {"members_per_gpu": wb, "solves_per_s": world * wb / (wms * 1e-3), "ms_per_step": wms,
                                    "frac_of_peak_per_gpu": F1 * wb / (wms * 1e-3) / 1e12 / peak, "scaling": "weak"}
-        del r
 
     if rank == 0 and world == 1 and not args.no_configs:
         out["configs"] = run_configs(torch, dev, m, peak)

@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return -(int)e_; } while (0)
 
@@ -265,7 +266,12 @@ static cudaError_t enqueue_jacobi_sweep(RJacobiParams rp, int nbmax, int batch, 
 // member is unconverged and sweeps are left -- no host read-back, and nothing at all runs when the divide-and-conquer SVD solved
 // every member.  Returns cudaErrorNotSupported-like errors to the caller, which then enqueues the sweeps unconditionally.
 static cudaError_t launch_jacobi_while_graph(const RJacobiParams& rp, int nbmax, int batch, int max_sweeps, unsigned long long* d_swoff,
-                                             int* d_done, double conv2, int* d_sweeps_left, cudaStream_t st) {
+                                             int* d_done, double conv2, int* d_sweeps_left, cudaStream_t st, int* host_us) {
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return (int)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+    const auto t0 = now();
+    auto t1 = t0, t2 = t0, t3 = t0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     cudaStream_t cap = nullptr;
@@ -305,14 +311,18 @@ static cudaError_t launch_jacobi_while_graph(const RJacobiParams& rp, int nbmax,
         capturing = false;
         if (e == cudaSuccess) e = e2;
         if (e != cudaSuccess) break;
+        t1 = now();
         if ((e = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess) break;
+        t2 = now();
         e = cudaGraphLaunch(exec, st);
+        t3 = now();
     } while (0);
     if (capturing) { cudaGraph_t ended = nullptr; cudaStreamEndCapture(cap, &ended); }
     if (exec) cudaGraphExecDestroy(exec);        // an executable graph in flight is released when it completes
     if (graph) cudaGraphDestroy(graph);
     if (cap) cudaStreamDestroy(cap);
     if (e != cudaSuccess) (void)cudaGetLastError();
+    if (host_us) { const auto t4 = now(); host_us[0] = us(t0, t1); host_us[1] = us(t1, t2); host_us[2] = us(t2, t3); host_us[3] = us(t3, t4); }
     return e;
 }
 
@@ -554,6 +564,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
     else     { bX = mat(0); bRs = mat(2); bLt = mat(3); bT1 = mat(0); bH = mat(1); bZ = mat(3); bXev = mat(0); bP = mat(4); bB = mat(5); bW = mat(0); }
     llck_launch_count = 0;
     int jacobi_graph = 0;
+    int graph_us[4] = {0, 0, 0, 0};     // host microseconds: build + capture, instantiate, launch, release
 
     // ---- metadata: per-member sizes and FID offsets go to the device through ONE staged copy; the call never waits for the stream ----
     int nbmax = 2;
@@ -654,7 +665,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
         int* d_sweeps_left = (int*)(ws + L.scalars);
         bool looped = false;
         if (!(flags & LLCK_FLAG_NO_GRAPH)) {
-            looped = launch_jacobi_while_graph(rp, nbmax, batch, max_sweeps, d_swoff, d_done, conv * conv, d_sweeps_left, st) == cudaSuccess;
+            looped = launch_jacobi_while_graph(rp, nbmax, batch, max_sweeps, d_swoff, d_done, conv * conv, d_sweeps_left, st, graph_us) == cudaSuccess;
             if (looped) { LLCK_LAUNCHED(); jacobi_graph = 1; }
         }
         if (!looped) {
@@ -874,6 +885,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
         for (int i = 0; i < 16; ++i) info[i] = 0;
         info[2] = ld; info[3] = nbmax;
         info[13] = llck_launch_count;                 // kernels enqueued by this call, counted at the launch sites
+        info[0] = graph_us[0]; info[5] = graph_us[1]; info[6] = graph_us[2]; info[7] = graph_us[3];
         info[14] = jacobi_graph;                      // 1: the Jacobi sweeps ran as a device-side WHILE graph node, 0: enqueued unconditionally
     }
     if (timing) {
