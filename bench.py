@@ -474,14 +474,24 @@ def run_configs(torch, dev, m, peak):
                                        "extrapolated_10k_members_s": 10000 * t / n5,
                                        "note": "host FIDs in, host records out through distributed.solve_ensemble_distributed"}
     del sig5
-    # wave boundary: 148 vs 149 members of m = 1024 (one-CTA-per-member kernels on 148 SMs)
+    # wave boundary: 148 vs 149 members of m = 1024 (one-CTA-per-member kernels on 148 SMs): as ONE launch sequence, and through the
+    # scheduler (ensemble.solve_chunks), which turns the nearly empty second wave into a thread-block-cluster chunk
     sigw = ensemble.to_device_complex(np.concatenate(workloads.pseudo_noise_members(workloads.brain_sim(2 * m, SIGMA, 0), range(149), SIGMA)), dev)
     pair = {}
     for nb in (148, 149):
         offw = np.arange(nb, dtype=np.int64) * 2 * m
-        ensemble.solve_device(sigw, offw, [m] * nb, [m] * nb, 1, 0.0, DWELL, sig_len=np.full(nb, 2 * m), want_mu=False)
-        t, _ = timed(lambda: ensemble.solve_device(sigw, offw, [m] * nb, [m] * nb, 1, 0.0, DWELL, sig_len=np.full(nb, 2 * m), want_mu=False), reps=2)
-        pair[str(nb)] = {"seconds": t, "solves_per_s": nb / t}
+        lenw = np.full(nb, 2 * m, dtype=np.int64)
+
+        def one_launch():
+            ensemble.solve_device(sigw, offw, [m] * nb, [m] * nb, 1, 0.0, DWELL, sig_len=lenw, want_mu=False)
+
+        def scheduled():
+            for _idx, _r in ensemble.solve_chunks(sigw, offw, lenw, [m] * nb, [m] * nb, 1, 0.0, DWELL, want_mu=False):
+                pass
+        one_launch(); scheduled()
+        t1, _ = timed(one_launch, reps=2)
+        t2, _ = timed(scheduled, reps=2)
+        pair[str(nb)] = {"one_launch_sequence_s": t1, "one_launch_solves_per_s": nb / t1, "scheduler_s": t2, "scheduler_solves_per_s": nb / t2}
     cfg["wave_boundary_m1024"] = pair
     return cfg
 

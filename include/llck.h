@@ -78,6 +78,10 @@ typedef struct llck_options {
 
 int llck_version(void);
 
+/* Waits for and releases the CUDA graphs earlier llck_kbdm_batched calls launched (see there).  Optional: every call releases
+ * the graphs of previous calls that have completed; call this before unloading the library or tearing the context down. */
+int llck_release_resources(void);
+
 /* Leading dimension used for every per-member matrix: round_up(max m, 64). */
 int llck_leading_dim(int m_max);
 
@@ -114,8 +118,9 @@ size_t llck_debug_offset(int batch, int ld, int which);
  * Asynchronous: returns once the launch sequence is enqueued on `stream` (LLCK_FLAG_TIMING makes it wait).  The Jacobi fallback
  * for members the divide-and-conquer SVD flags is ONE CUDA-graph launch whose conditional WHILE node repeats the sweep on the
  * device until every member has converged (at most llck_options.jacobi_max_sweeps times; zero times when no member was flagged),
- * so no decision needs a device-to-host read-back.  (A small graph is built and released inside the call: host-side objects
- * only, no device memory.)
+ * so no decision needs a device-to-host read-back.  (A small graph is built inside the call -- host-side objects, no device
+ * memory -- and, because an executable graph cannot be destroyed while in flight without blocking, released by a later call or
+ * by llck_release_resources() once its launch has completed: the library's only process-wide state.)
  */
 int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int64_t* sig_len, const int32_t* m, const int32_t* l,
                       int32_t p, double q, double dwell, int32_t batch,

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libllck.so")
 
 SYMBOLS = (
     "llck_version",
+    "llck_release_resources",
     "llck_leading_dim",
     "llck_workspace_bytes",
     "llck_debug_offset",
@@ -78,6 +79,8 @@ def load():
     c_int, c_i64, c_sz, c_vp, c_dbl = ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_double
     lib.llck_version.restype = c_int
     lib.llck_version.argtypes = []
+    lib.llck_release_resources.restype = c_int
+    lib.llck_release_resources.argtypes = []
     lib.llck_leading_dim.restype = c_int
     lib.llck_leading_dim.argtypes = [c_int]
     lib.llck_workspace_bytes.restype = c_sz

@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <chrono>
+#include <mutex>
+#include <vector>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return -(int)e_; } while (0)
 
@@ -249,6 +251,29 @@ static int bidiag_driver(cplx* A, cplx* Q, cplx* P, long long stride, int ld, co
     return 0;
 }
 
+// Executable graphs cannot be destroyed while in flight without blocking the caller (measured: cudaGraphExecDestroy right after
+// cudaGraphLaunch waits for the graph), so a launched graph is parked here with an event recorded behind it and released by a
+// later call -- or by llck_release_resources() -- once that event has completed.  This is the library's only process-wide state:
+// host-side handles awaiting release, never read by the computation.
+struct PendingGraph { cudaGraphExec_t exec; cudaGraph_t graph; cudaEvent_t done; };
+static std::mutex g_pending_mu;
+static std::vector<PendingGraph> g_pending;
+
+static void reap_pending_graphs(bool wait) {
+    std::lock_guard<std::mutex> lock(g_pending_mu);
+    size_t keep = 0;
+    for (size_t i = 0; i < g_pending.size(); ++i) {
+        PendingGraph& pg = g_pending[i];
+        cudaError_t q = wait ? cudaEventSynchronize(pg.done) : cudaEventQuery(pg.done);
+        if (q == cudaErrorNotReady) { g_pending[keep++] = pg; continue; }
+        if (q != cudaSuccess) (void)cudaGetLastError();
+        cudaGraphExecDestroy(pg.exec);
+        cudaGraphDestroy(pg.graph);
+        cudaEventDestroy(pg.done);
+    }
+    g_pending.resize(keep);
+}
+
 // One Jacobi sweep on `st` (all rounds + the convergence bookkeeping); CTAs of converged members exit at once.
 static cudaError_t enqueue_jacobi_sweep(RJacobiParams rp, int nbmax, int batch, unsigned long long* d_swoff, int* d_done, double conv2, cudaStream_t st) {
     for (int r = 0; r < nbmax - 1; ++r) {
@@ -318,9 +343,24 @@ static cudaError_t launch_jacobi_while_graph(const RJacobiParams& rp, int nbmax,
         t3 = now();
     } while (0);
     if (capturing) { cudaGraph_t ended = nullptr; cudaStreamEndCapture(cap, &ended); }
-    if (exec) cudaGraphExecDestroy(exec);        // an executable graph in flight is released when it completes
-    if (graph) cudaGraphDestroy(graph);
-    if (cap) cudaStreamDestroy(cap);
+    if (cap) cudaStreamDestroy(cap);             // nothing ever ran on the capture stream
+    bool parked = false;
+    if (e == cudaSuccess && exec) {
+        cudaEvent_t done = nullptr;
+        if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) == cudaSuccess) {
+            if (cudaEventRecord(done, st) == cudaSuccess) {
+                std::lock_guard<std::mutex> lock(g_pending_mu);
+                g_pending.push_back({exec, graph, done});
+                parked = true;
+            } else {
+                cudaEventDestroy(done);
+            }
+        }
+    }
+    if (!parked) {                               // error path (or no event): blocking release
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+    }
     if (e != cudaSuccess) (void)cudaGetLastError();
     if (host_us) { const auto t4 = now(); host_us[0] = us(t0, t1); host_us[1] = us(t1, t2); host_us[2] = us(t2, t3); host_us[3] = us(t3, t4); }
     return e;
@@ -329,6 +369,11 @@ static cudaError_t launch_jacobi_while_graph(const RJacobiParams& rp, int nbmax,
 extern "C" {
 
 int llck_version(void) { return LLCK_VERSION; }
+
+int llck_release_resources(void) {
+    reap_pending_graphs(true);
+    return 0;
+}
 
 int llck_leading_dim(int m_max) { return ((m_max + 63) / 64) * 64; }
 
@@ -563,6 +608,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
     if (dbg) { bX = mat(0); bRs = mat(2); bLt = mat(3); bT1 = mat(4); bH = mat(8); bZ = mat(9); bXev = mat(10); bP = mat(11); bB = mat(12); bW = mat(13); }
     else     { bX = mat(0); bRs = mat(2); bLt = mat(3); bT1 = mat(0); bH = mat(1); bZ = mat(3); bXev = mat(0); bP = mat(4); bB = mat(5); bW = mat(0); }
     llck_launch_count = 0;
+    reap_pending_graphs(false);         // release graphs of earlier calls whose launch has completed (non-blocking)
     int jacobi_graph = 0;
     int graph_us[4] = {0, 0, 0, 0};     // host microseconds: build + capture, instantiate, launch, release
 

@@ -75,20 +75,38 @@ def max_chunk(ld, device=None, reserve_frac=0.8, flags=0):
 
 
 def plan_chunks(M, cap, wave=148):
-    """Chunk size for M members when at most ``cap`` fit in memory: as few chunks as possible, of equal size, rounded up to a
-    whole number of waves of the one-CTA-per-member kernels (``wave`` = SM count) so that no chunk ends in a nearly empty wave."""
+    """Chunk sizes (a list summing to M) for M members when at most ``cap`` fit in memory.  The one-CTA-per-member kernels run
+    in waves of ``wave`` (= SM count) members: chunks are as few and as equal as possible and whole numbers of waves, and a
+    remainder of at most half a wave becomes its own small chunk, which the library runs with a thread-block CLUSTER per member
+    (batches <= 74) instead of leaving a nearly empty last wave of single CTAs."""
     cap = max(1, int(cap))
-    if M <= cap:
-        return M
-    nchunks = -(-M // cap)
-    size = -(-M // nchunks)
-    if wave > 0 and size > wave:
-        rounded = -(-size // wave) * wave
-        if rounded <= cap:
-            size = rounded
-        elif (cap // wave) * wave > 0:
-            size = (cap // wave) * wave
-    return min(size, cap)
+    M = int(M)
+    if M <= 0:
+        return []
+    if wave <= 0 or M <= wave or cap < wave:
+        sizes, left = [], M
+        n = -(-M // cap)
+        for i in range(n):
+            s = -(-left // (n - i))
+            sizes.append(s)
+            left -= s
+        return sizes
+    tail = M % wave
+    split_tail = 0 < tail <= wave // 2
+    body = M - tail if split_tail else M
+    cap_w = (cap // wave) * wave                                    # whole waves that fit
+    n = -(-body // cap_w)
+    sizes, left = [], body
+    for i in range(n):
+        s = -(-left // (n - i))
+        s = min(-(-s // wave) * wave, cap_w, left)
+        sizes.append(s)
+        left -= s
+        if left <= 0:
+            break
+    if split_tail:
+        sizes.append(tail)
+    return sizes
 
 
 def sm_count(device=None):
@@ -109,12 +127,16 @@ def solve_chunks(sig_dev, offsets, lens, m, l, p, q, dwell, chunk=None, want_mu=
     dev = sig_dev.device
     if chunk is None:
         ld = lib.llck_leading_dim(int(m.max()))
-        chunk = plan_chunks(M, max_chunk(ld, dev, flags=flags), sm_count(dev))
+        sizes = plan_chunks(M, max_chunk(ld, dev, flags=flags), sm_count(dev))
+    else:
+        sizes = [min(int(chunk), M - c0) for c0 in range(0, M, int(chunk))]
     if order is None:
         # cost-sorted chunks keep similar sizes together (less padding work inside a launch); one chunk keeps the caller's order
-        order = np.arange(M) if chunk >= M else np.argsort(-(m.astype(np.int64) * 4096 + l), kind="stable")
-    for c0 in range(0, M, chunk):
-        idx = order[c0:c0 + chunk]
+        order = np.arange(M) if len(sizes) == 1 else np.argsort(-(m.astype(np.int64) * 4096 + l), kind="stable")
+    c0 = 0
+    for size in sizes:
+        idx = order[c0:c0 + size]
+        c0 += size
         yield idx, solve_device(sig_dev, offsets[idx], m[idx], l[idx], p, q, dwell, flags=flags, want_mu=want_mu,
                                 sig_len=lens[idx], options=options)
 
@@ -137,7 +159,11 @@ def get_workspace(nbytes, dev):
 
 
 def release_workspace(dev=None):
-    """Drop the cached solver workspace of ``dev`` (all devices if None)."""
+    """Drop the cached solver workspace of ``dev`` (all devices if None) and release the library's parked CUDA graphs."""
+    try:
+        _native.load().llck_release_resources()
+    except Exception:  # noqa: BLE001
+        pass
     if dev is None:
         _WORKSPACES.clear()
         return

@@ -133,12 +133,19 @@ def test_lpt_shards_balance_and_cover():
 
 
 def test_plan_chunks_whole_waves():
-    assert plan_chunks(100, 780) == 100                      # fits: one chunk
-    assert plan_chunks(1184, 780) == 592                     # two equal chunks of 4 waves, not 780 + 404
-    assert plan_chunks(10000, 780) % 148 == 0 and plan_chunks(10000, 780) <= 780
-    assert plan_chunks(65536, 3000) % 148 == 0
-    assert plan_chunks(300, 100) == 100                      # memory cap below one wave
-    assert plan_chunks(7, 3) == 3
+    assert plan_chunks(100, 780) == [100]                    # fits: one chunk
+    assert plan_chunks(1184, 780) == [592, 592]              # two equal chunks of 4 waves, not 780 + 404
+    assert plan_chunks(148, 780) == [148] and plan_chunks(296, 780) == [296]
+    assert plan_chunks(149, 780) == [148, 1]                 # a nearly empty second wave becomes a cluster-mode chunk
+    assert plan_chunks(200, 780) == [148, 52]
+    assert plan_chunks(240, 780) == [240]                    # the last wave is more than half full: leave it
+    for M, cap in ((10000, 780), (65536, 3000), (1185, 780), (5000, 200)):
+        sizes = plan_chunks(M, cap)
+        assert sum(sizes) == M and max(sizes) <= cap and min(sizes) > 0
+        assert all(s % 148 == 0 for s in sizes[:-2])
+    assert plan_chunks(300, 100) == [100, 100, 100]          # memory cap below one wave
+    assert plan_chunks(7, 3) == [3, 2, 2]
+    assert plan_chunks(0, 10) == []
 
 
 def test_flatten_signals():
