@@ -1,23 +1,24 @@
 #!/bin/bash
 # ncu evidence for profiles/: launch list of the bench command (+ with "full": --set full captures of the heaviest kernels).
-# usage: bash tools/ncu_pass.sh TAG [full]
+# usage: bash tools/ncu_pass.sh TAG [full]      (one GPU; never under torchrun)
 set -x
-TAG=${1:-r01c}
+TAG=${1:-r02a}
 CMD="python bench.py --steps 1 --warmup 1 --members 148 --e2e-steps 1 --no-cpu-baseline --no-configs --no-weak"
-$CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
+$CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; exit 1; }
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "list rc=$?"
 if [ "$2" = "full" ]; then
   cap() {   # name regex skip
-    ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c 1 -f -o gpurun_out/prof_${TAG}_$1 $CMD > gpurun_out/ncu_${TAG}_$1.log 2>&1
+    timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c 1 -f -o gpurun_out/prof_${TAG}_$1 $CMD > gpurun_out/ncu_${TAG}_$1.log 2>&1
     echo "$1 rc=$?"
   }
   cap hqr hqr_kernel 0
   cap bidiag bidiag_panel 8
   cap hess hess_panel 8
-  cap bdcgemm bdc_gemm 4
-  cap bdcsecular bdc_secular 4
   cap hankel "zgemm_batched_kernel<2" 0
+  cap rankk "zgemm_rankk_kernel<32" 20
+  cap bdcgemm bdc_gemm 4
   ls -la gpurun_out/*_${TAG}_*.ncu-rep
+  python tools/ncu_summary.py gpurun_out/ncu_summary_$TAG.md gpurun_out/prof_${TAG}_*.ncu-rep
 fi
 echo "done"

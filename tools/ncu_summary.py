@@ -1,5 +1,6 @@
-"""Summarise .ncu-rep captures into a small markdown table: python tools/ncu_summary.py out.md rep1 rep2 ..."""
-import csv, subprocess, sys, io
+"""Summarise .ncu-rep captures into a small markdown table: python tools/ncu_summary.py out.md rep1 rep2 ...
+A capture of hqr_kernel also writes <dir of out.md>/hqr_traffic.json (DRAM bytes per launch: bench.py's roofline.traffic)."""
+import csv, json, os, subprocess, sys, io
 WANT = [
     ("duration", "gpu__time_duration.sum"),
     ("dram read", "dram__bytes_read.sum"),
@@ -29,6 +30,19 @@ for rep in sys.argv[2:]:
             cells.append(f"{row[i]} {units[i]}".strip())
         else:
             cells.append("n/a")
-    out.append("| " + row[hdr.index("Kernel Name")].split("(")[0] + " | " + " | ".join(cells) + " |")
+    name = row[hdr.index("Kernel Name")].split("(")[0]
+    out.append("| " + name + " | " + " | ".join(cells) + " |")
+    if name.startswith("hqr_kernel"):
+        def val(key):
+            i = hdr.index(key)
+            v = float(row[i].replace(",", ""))
+            u = units[i].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(u, 1)
+        grid = int(float(row[hdr.index("launch__grid_size")].replace(",", "")))
+        json.dump({"kernel": "hqr_kernel", "m": 1024, "members_per_launch": grid,
+                   "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                   "duration_ns_under_ncu": row[hdr.index("gpu__time_duration.sum")],
+                   "source": "ncu --set full capture " + os.path.basename(rep) + " (tools/ncu_pass.sh, bench --members 148 --m 1024)"},
+                  open(os.path.join(os.path.dirname(os.path.abspath(sys.argv[1])), "hqr_traffic.json"), "w"), indent=1)
 open(sys.argv[1], "w").write("\n".join(out) + "\n")
 print("\n".join(out))
