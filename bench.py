@@ -434,6 +434,7 @@ def run_configs(torch, dev, m, peak):
     t_full, r3 = timed(lambda: llc_kbdm(c2, DWELL, m2), reps=2)
     cfg["c2_llc_ensemble"] = {"members": 100, "m_range": "700..1024", "solve_phase_s": t, "solve_frac_of_peak": frac(m2, m2, t),
                               "total_with_clustering_s": t_full, "clusters": int(len(r3.line_list)),
+                              "stage_seconds_last_call": dict(__import__("llckbdm_b200.llckbdm", fromlist=["x"]).LAST_STAGE_SECONDS),
                               "bad_status_members": int((r2.status != 0).sum()), "host_cores": os.cpu_count(),
                               "note": "solve_phase_s: host FID in, host line lists out; total_with_clustering_s: llc_kbdm end to end, best of 2 "
                                       "(device solves, pooling, HDBSCAN spanning trees, silhouettes, RMSE selection; dendrogram condensation / "

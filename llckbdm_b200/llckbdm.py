@@ -49,6 +49,8 @@ CLUSTER_BACKEND = "device"
 # worker threads / processes of the host halves (0 = all cores)
 CLUSTER_JOBS = 0
 MIN_CLUSTER_SIZE = 5           # hdbscan.HDBSCAN default, never changed by the reference
+# wall-clock seconds of the stages of the last llc_kbdm call (profiling aid: solve+pool, spanning trees, labelling, silhouettes+averages, rmse)
+LAST_STAGE_SECONDS = {}
 
 
 @attr.s(auto_attribs=True)
@@ -91,17 +93,25 @@ def _llc_kbdm_device(sig_dev, dwell, ms, ls, p, q):
     feature transform, spanning trees, silhouettes and the min-RMSE selection all read it there; only line lists, labels and
     silhouettes (kilobytes) cross to the host."""
     torch = _require_cuda()
+    import time
+    t0 = time.perf_counter()
+    LAST_STAGE_SECONDS.clear()
     if q > 0:
         logger.debug('Using Tikhonov Regularization with q=%f', q)
     # sampling + pooling + filter + feature transform (reference llckbdm.py:76-98) in one device pass
     samples, features, status = solve_pooled(sig_dev, ms, ls, p, q, dwell)
+    LAST_STAGE_SECONDS["solve_pool"] = time.perf_counter() - t0
     for k, mm in enumerate(ms):
         raise_for_status(int(status[k]), mm)
     if len(samples) == 0:
         return LlcKbdmResult()
     # HDBSCAN for min_samples = 1..M-1 (reference llckbdm.py:104-116): all fits at once
+    t1 = time.perf_counter()
     labelings = _fit_all(features, list(range(1, len(ms))))
+    t2 = time.perf_counter()
     results = _results_from_labelings(samples, features, labelings)
+    t3 = time.perf_counter()
+    LAST_STAGE_SECONDS.update(hdbscan_fits=t2 - t1, silhouettes_averages=t3 - t2, pooled_points=int(len(samples)))
     if not results:
         return LlcKbdmResult()
     # min-RMSE selection over the cluster averages (reference llckbdm.py:120-124 -> min_rmse_kbdm.py:33-55) on the device
@@ -120,6 +130,7 @@ def _llc_kbdm_device(sig_dev, dwell, ms, ls, p, q):
     for i, rmse in enumerate(rmses):
         logger.debug('RMSE for sample #%d: %f', i, rmse)
     k = int(np.argmin(rmses))
+    LAST_STAGE_SECONDS["rmse_selection"] = time.perf_counter() - t3
     return LlcKbdmResult(line_list=cands[k], rmse=float(rmses[k]), silhouette=np.array(results[k].clustered_silhouettes))
 
 
@@ -269,9 +280,14 @@ def _fit_all(features, min_samples_list):
     n = len(features)
     if _gpu_fit_supported(features, min_samples_list):
         # neighbour counts INCLUDING the point itself (see the module docstring)
+        import time
         ks = [min(int(ms), n - 1) + 1 for ms in min_samples_list]
+        t0 = time.perf_counter()
         src, dst, w = hdbscan_msts_device(features, ks)
-        return _labels_from_msts(src, dst, w)
+        t1 = time.perf_counter()
+        labels = _labels_from_msts(src, dst, w)
+        LAST_STAGE_SECONDS.update(spanning_trees=t1 - t0, labelling=time.perf_counter() - t1)
+        return labels
     jobs = CLUSTER_JOBS or min(n_fits, os.cpu_count() or 1)
     if not (jobs > 1 and n_fits >= 8 and n >= 4000):
         return [_fit_one(features, ms) for ms in min_samples_list]
