@@ -184,10 +184,14 @@ int llck_pool_features(const double* line_lists, int64_t ll_stride, const int32_
  * llck_hdbscan_mst:            Prim's spanning tree of the mutual-reachability graph max(core[a], core[b], |a - b|) for `nfits`
  *                              fits at once (replaces mst_from_data_matrix per fit); core_row[f] selects the row of `core`
  *                              (= min_samples - 1); edges in insertion order into mst_src / mst_dst / mst_w [nfits][n-1];
- *                              min_reach [nfits][n] and cur_src [nfits][n] are scratch.  n <= 131072.  Stream-ordered, asynchronous.  */
+ *                              min_reach [nfits][n] and cur_src [nfits][n] are scratch.  n <= 131072.  Stream-ordered, asynchronous.
+ *                              Up to 57,344 points a fit runs on a thread-block cluster of 8 CTAs with its points resident in
+ *                              shared memory and registers (no global traffic per step); larger sets, or LLCK_MST_SINGLE_CTA,
+ *                              use one CTA per fit that streams the points from L2.  Both give bit-identical edges.        */
 int llck_hdbscan_core_distances(const double* X, int32_t n, int32_t kmax, double* core, void* stream);
+#define LLCK_MST_SINGLE_CTA 1         /* llck_hdbscan_mst flags: always use the one-CTA-per-fit kernel */
 int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32_t* core_row, int32_t nfits,
-                     double* min_reach, int32_t* cur_src, int64_t* mst_src, int64_t* mst_dst, double* mst_w, void* stream);
+                     double* min_reach, int32_t* cur_src, int64_t* mst_src, int64_t* mst_dst, double* mst_w, int32_t flags, void* stream);
 
 /* HOST function: flat cluster labels of `nfits` HDBSCAN fits from their spanning trees -- the rest of every fit of
  * llckbdm/llckbdm.py:280-283 after the spanning tree (single-linkage dendrogram, condensed tree, stabilities, excess-of-mass

@@ -32,6 +32,7 @@ SYMBOLS = (
 FLAG_DEBUG_KEEP = 1
 FLAG_TIMING = 2
 FLAG_NO_GRAPH = 4
+MST_SINGLE_CTA = 1
 
 E_BADARG = 1
 E_WORKSPACE = 2
@@ -113,7 +114,7 @@ def load():
     lib.llck_hdbscan_core_distances.restype = c_int
     lib.llck_hdbscan_core_distances.argtypes = [c_vp, c_int, c_int, c_vp, c_vp]
     lib.llck_hdbscan_mst.restype = c_int
-    lib.llck_hdbscan_mst.argtypes = [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.llck_hdbscan_mst.argtypes = [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]
     lib.llck_hdbscan_labels.restype = c_int
     lib.llck_hdbscan_labels.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]
     lib.llck_multi_fid_batched.restype = c_int

@@ -479,11 +479,31 @@ int llck_hdbscan_core_distances(const double* X, int32_t n, int32_t kmax, double
 }
 
 int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32_t* core_row, int32_t nfits,
-                     double* min_reach, int32_t* cur_src, int64_t* mst_src, int64_t* mst_dst, double* mst_w, void* stream) {
+                     double* min_reach, int32_t* cur_src, int64_t* mst_src, int64_t* mst_dst, double* mst_w, int32_t flags, void* stream) {
     if (!X || !core || !core_row || !min_reach || !cur_src || !mst_src || !mst_dst || !mst_w) return LLCK_E_BADARG;
     if (n < 2 || n > HDB_PRIM_THREADS * 128 || nfits < 1) return LLCK_E_BADARG;
-    hdb_prim_kernel<<<nfits, HDB_PRIM_THREADS, 0, (cudaStream_t)stream>>>(X, n, core, core_row, min_reach, cur_src,
-                                                                          (long long*)mst_src, (long long*)mst_dst, mst_w);
+    cudaStream_t st = (cudaStream_t)stream;
+    // one thread-block cluster per fit with the points resident in shared memory / registers, when they fit
+    const int pt = (n + HDB_CS * HDB_PRIM_THREADS - 1) / (HDB_CS * HDB_PRIM_THREADS);
+    if (pt <= HDB_PT_MAX && !(flags & LLCK_MST_SINGLE_CTA)) {
+        const size_t smem = (size_t)pt * HDB_PRIM_THREADS * sizeof(double4) + 2 * HDB_CS * sizeof(HdbCand);
+        if (cudaFuncSetAttribute(hdb_prim_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute attr[1];
+            cfg.blockDim = dim3(HDB_PRIM_THREADS); cfg.dynamicSmemBytes = smem; cfg.gridDim = dim3(nfits * HDB_CS); cfg.stream = st;
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = HDB_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, hdb_prim_cluster_kernel, &cfg) == cudaSuccess && nclusters >= 1) {
+                CK(cudaLaunchKernelEx(&cfg, hdb_prim_cluster_kernel, X, (int)n, core, core_row, pt, (long long*)mst_src, (long long*)mst_dst, mst_w));
+                return 0;
+            }
+        }
+        (void)cudaGetLastError();
+    }
+    hdb_prim_kernel<<<nfits, HDB_PRIM_THREADS, 0, st>>>(X, n, core, core_row, min_reach, cur_src,
+                                                        (long long*)mst_src, (long long*)mst_dst, mst_w);
     CK(cudaGetLastError());
     return 0;
 }

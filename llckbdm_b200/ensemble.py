@@ -303,7 +303,7 @@ def solve_pooled(signal, m, l, p, q, dwell, device=None, chunk=None, amplitude_t
     return (np.concatenate([pm[0] for pm in per_member]), np.concatenate([pm[1] for pm in per_member]), status)
 
 
-def hdbscan_msts_device(features, min_samples_list, device=None):
+def hdbscan_msts_device(features, min_samples_list, device=None, single_cta=False):
     """Core distances (one brute-force pass for all k) and Prim spanning trees of the mutual-reachability graph for every
     min_samples value at once (llck_hdbscan_core_distances / llck_hdbscan_mst), edge-for-edge what
     sklearn.cluster._hdbscan._linkage.mst_from_data_matrix returns for the same points.
@@ -327,7 +327,8 @@ def hdbscan_msts_device(features, min_samples_list, device=None):
         dst = torch.empty((F, n - 1), dtype=torch.int64, device=dev)
         w = torch.empty((F, n - 1), dtype=torch.float64, device=dev)
         _native.check_rc(lib.llck_hdbscan_mst(Xd.data_ptr(), n, core.data_ptr(), rows.data_ptr(), F, mr.data_ptr(), cs.data_ptr(),
-                                              src.data_ptr(), dst.data_ptr(), w.data_ptr(), st), "llck_hdbscan_mst")
+                                              src.data_ptr(), dst.data_ptr(), w.data_ptr(),
+                                              _native.MST_SINGLE_CTA if single_cta else 0, st), "llck_hdbscan_mst")
         return src.cpu().numpy(), dst.cpu().numpy(), w.cpu().numpy()
 
 

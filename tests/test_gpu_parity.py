@@ -213,7 +213,9 @@ def test_gpu_hdbscan_spanning_trees_give_identical_labels(cuda):
     X[100:110, :3] = np.round(X[100:110, :3], 1)   # coarse grid: exact distance ties
     from sklearn.cluster import HDBSCAN
     ks = [1, 2, 5, 9, 33]                          # neighbour counts INCLUDING the point itself (sklearn's min_samples)
-    src, dst, w = hdbscan_msts_device(X, ks)
+    src, dst, w = hdbscan_msts_device(X, ks)                      # thread-block cluster per fit, points resident on chip
+    src1, dst1, w1 = hdbscan_msts_device(X, ks, single_cta=True)  # one CTA per fit streaming from L2 (large point sets)
+    assert np.array_equal(src, src1) and np.array_equal(dst, dst1) and np.array_equal(w, w1)
     for f, k in enumerate(ks):
         cd = np.ascontiguousarray(NearestNeighbors(n_neighbors=k, algorithm="kd_tree").fit(X).kneighbors(X, k)[0][:, -1])
         ref = mst_from_data_matrix(np.asarray(X, order="C"), cd, DistanceMetric.get_metric("euclidean"), 1.0)
