@@ -185,7 +185,7 @@ int llck_pool_features(const double* line_lists, int64_t ll_stride, const int32_
  *                              fits at once (replaces mst_from_data_matrix per fit); core_row[f] selects the row of `core`
  *                              (= min_samples - 1); edges in insertion order into mst_src / mst_dst / mst_w [nfits][n-1];
  *                              min_reach [nfits][n] and cur_src [nfits][n] are scratch.  n <= 131072.  Stream-ordered, asynchronous.
- *                              Up to 57,344 points a fit runs on a thread-block cluster of 8 CTAs with its points resident in
+ *                              Up to 45,056 points a fit runs on a thread-block cluster of 8 CTAs with its points resident in
  *                              shared memory and registers (no global traffic per step); larger sets, or LLCK_MST_SINGLE_CTA,
  *                              use one CTA per fit that streams the points from L2.  Both give bit-identical edges.        */
 int llck_hdbscan_core_distances(const double* X, int32_t n, int32_t kmax, double* core, void* stream);

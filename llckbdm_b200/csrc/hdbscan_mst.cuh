@@ -85,9 +85,15 @@ __global__ void __launch_bounds__(HDB_PRIM_THREADS) hdb_prim_kernel(const double
             if (visited) continue;
             double m = mr[j];
             int src = cs[j];
-            const double pd = __dsqrt_rn(hdb_rdist(xc, reinterpret_cast<const double4*>(X)[j]));
-            const double mrd = fmax(fmax(cd, cr[j]), pd);
-            if (mrd < m) { m = mrd; src = cur; mr[j] = m; cs[j] = cur; }
+            // skip the coordinate load, distance and square root when they cannot lower m (see hdb_prim_cluster_kernel)
+            const double lb = fmax(cd, cr[j]);
+            if (lb < m) {
+                const double d2 = hdb_rdist(xc, reinterpret_cast<const double4*>(X)[j]);
+                if (d2 < m * m * 1.0000000000000009) {
+                    const double mrd = fmax(lb, __dsqrt_rn(d2));
+                    if (mrd < m) { m = mrd; src = cur; mr[j] = m; cs[j] = cur; }
+                }
+            }
             if (m < bv) { bv = m; bj = j; bs = src; }            // ascending j within a thread: strict < keeps the lowest index
         }
         // lexicographic (value, index) minimum over the CTA == the sequential scan's "first strictly smaller" rule
@@ -125,42 +131,60 @@ __global__ void __launch_bounds__(HDB_PRIM_THREADS) hdb_prim_kernel(const double
 // (coordinates, core distance, running minimum, source: 52 B) from L2 in each of the n-1 steps -- 99 fits x 43k points is
 // L2-bandwidth bound.  Here every CTA keeps its share of the points in shared memory (coordinates) and registers (core distance,
 // running minimum, source, visited bit), so a step touches no global memory except the edge it appends:
-//   per step: update own points against the current node -> CTA-wide lexicographic (value, index) minimum -> the CTA's
-//   candidate (value, index, source, coordinates and core distance of the candidate) is stored into every peer's shared memory
-//   (distributed shared memory) -> ONE cluster barrier -> every CTA picks the winner of the HDB_CS candidates redundantly.
+//   per step: update own points against the current node -> CTA-wide lexicographic (value, index) minimum (warp level: integer
+//   redux on the bit pattern of the non-negative distances) -> the CTA's candidate (value, index, source, coordinates and core
+//   distance of the candidate) is stored into every peer's shared memory (distributed shared memory) -> ONE cluster barrier ->
+//   every CTA picks the winner of the HDB_CS candidates redundantly.
 // Same arithmetic and the same tie rule as hdb_prim_kernel: the edge lists are bit-identical.
-// Limits: n <= HDB_CS * HDB_PRIM_THREADS * HDB_PT_MAX points (57,344); larger sets use hdb_prim_kernel.
-// dynamic smem: pt * HDB_PRIM_THREADS * 32 B (coordinates) + 2 * HDB_CS candidate records
+// Limits: n <= HDB_CS * HDB_CT * HDB_PT_MAX points (45,056); larger sets use hdb_prim_kernel.
+// dynamic smem: pt * HDB_CT * 32 B (coordinates) + 2 * HDB_CS candidate records
 #define HDB_CS 8
-#define HDB_PT_MAX 7
+#define HDB_CT 512           // threads per CTA
+#define HDB_PT_MAX 11        // own points per thread
 struct __align__(16) HdbCand { double v; int j; int s; double4 x; double cd; double pad; };
 
-__global__ void __launch_bounds__(HDB_PRIM_THREADS, 1) hdb_prim_cluster_kernel(const double* __restrict__ X, int n, const double* __restrict__ core,
-                                                                               const int* __restrict__ core_row, int pt,
-                                                                               long long* __restrict__ mst_src, long long* __restrict__ mst_dst,
-                                                                               double* __restrict__ mst_w) {
+// lexicographic (value, index) minimum over a warp for non-negative doubles: their bit patterns order like the values
+__device__ __forceinline__ void hdb_warp_argmin(double& bv, int& bj, int& bs, double& bc) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong(bv);
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const bool is_min = (hi == mhi) && (lo == mlo);
+    const int mj = __reduce_min_sync(0xffffffffu, is_min ? bj : 0x7fffffff);
+    const unsigned who = __ballot_sync(0xffffffffu, is_min && bj == mj);
+    const int srcl = __ffs(who) - 1;
+    bv = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+    bj = mj;
+    bs = __shfl_sync(0xffffffffu, bs, srcl);
+    bc = __shfl_sync(0xffffffffu, bc, srcl);
+}
+
+__global__ void __launch_bounds__(HDB_CT, 1) hdb_prim_cluster_kernel(const double* __restrict__ X, int n, const double* __restrict__ core,
+                                                                     const int* __restrict__ core_row, int pt,
+                                                                     long long* __restrict__ mst_src, long long* __restrict__ mst_dst,
+                                                                     double* __restrict__ mst_w) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double4* xs = reinterpret_cast<double4*>(smem_raw);                                    // [pt][1024] own coordinates
-    HdbCand* recs = reinterpret_cast<HdbCand*>(xs + (size_t)pt * HDB_PRIM_THREADS);         // [2][HDB_CS]
-    __shared__ double rv[32];
-    __shared__ int rj[32], rs[32];
-    __shared__ double s_cd;
+    double4* xs = reinterpret_cast<double4*>(smem_raw);                                    // [pt][HDB_CT] own coordinates
+    HdbCand* recs = reinterpret_cast<HdbCand*>(xs + (size_t)pt * HDB_CT);                   // [2][HDB_CS]
+    constexpr int NW = HDB_CT / 32;
+    __shared__ double rv[NW], rc[NW];
+    __shared__ int rj[NW], rs[NW];
     const int f = blockIdx.x / HDB_CS, crank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* cr = core + (long long)core_row[f] * n;
-    const int per_cta = pt * HDB_PRIM_THREADS;
+    const int per_cta = pt * HDB_CT;
     const int base = crank * per_cta;                       // this CTA owns points [base, base + per_cta)
     double mr[HDB_PT_MAX], crj[HDB_PT_MAX];
     int cs[HDB_PT_MAX];
     unsigned live = 0u;                                      // bit q: own point q exists and is not visited yet
 #pragma unroll
     for (int q = 0; q < HDB_PT_MAX; ++q) {
-        const int j = base + tid + HDB_PRIM_THREADS * q;
+        const int j = base + tid + HDB_CT * q;
         mr[q] = INFINITY; cs[q] = 1; crj[q] = 0.0;
         if (q < pt && j < n) {
-            xs[tid + HDB_PRIM_THREADS * q] = reinterpret_cast<const double4*>(X)[j];
+            xs[tid + HDB_CT * q] = reinterpret_cast<const double4*>(X)[j];
             crj[q] = cr[j];
             if (j != 0) live |= 1u << q;                     // node 0 is the start: visited
         }
@@ -170,71 +194,62 @@ __global__ void __launch_bounds__(HDB_PRIM_THREADS, 1) hdb_prim_cluster_kernel(c
     int cur = 0;
     cluster.sync();
     for (int i = 0; i < n - 1; ++i) {
-        double bv = 1.7976931348623157e308;                  // DBL_MAX: candidates must be strictly below it
-        int bj = 0, bs = 0;
+        double bv = 1.7976931348623157e308, bc = 0.0;        // DBL_MAX: candidates must be strictly below it
+        int bj = 0x7ffffffe, bs = 0;
 #pragma unroll
         for (int q = 0; q < HDB_PT_MAX; ++q) {
             if ((live >> q) & 1u) {
-                const int j = base + tid + HDB_PRIM_THREADS * q;
-                const double pd = __dsqrt_rn(hdb_rdist(xc, xs[tid + HDB_PRIM_THREADS * q]));
-                const double mrd = fmax(fmax(cd, crj[q]), pd);
-                if (mrd < mr[q]) { mr[q] = mrd; cs[q] = cur; }
-                if (mr[q] < bv) { bv = mr[q]; bj = j; bs = cs[q]; }          // ascending j within a thread: strict < keeps the lowest index
+                // mutual reachability max(cd, cr_j, |x_c - x_j|) replaces mr[q] only if it is strictly smaller: when a core distance
+                // already reaches mr[q], or the SQUARED distance clearly exceeds mr[q]^2, nothing changes and the (expensive, FP64
+                // pipe bound) distance / square root are skipped -- results are unchanged, the margin covers the roundings
+                const double m_old = mr[q], lb = fmax(cd, crj[q]);
+                if (lb < m_old) {
+                    const double d2 = hdb_rdist(xc, xs[tid + HDB_CT * q]);
+                    if (d2 < m_old * m_old * 1.0000000000000009) {
+                        const double mrd = fmax(lb, __dsqrt_rn(d2));
+                        if (mrd < m_old) { mr[q] = mrd; cs[q] = cur; }
+                    }
+                }
+                if (mr[q] < bv) { bv = mr[q]; bj = base + tid + HDB_CT * q; bs = cs[q]; bc = crj[q]; }   // ascending j: strict < keeps the lowest index
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oj = __shfl_xor_sync(0xffffffffu, bj, o), os = __shfl_xor_sync(0xffffffffu, bs, o);
-            if (ov < bv || (ov == bv && ov < 1.7976931348623157e308 && oj < bj)) { bv = ov; bj = oj; bs = os; }
-        }
-        if (lane == 0) { rv[warp] = bv; rj[warp] = bj; rs[warp] = bs; }
+        hdb_warp_argmin(bv, bj, bs, bc);
+        if (lane == 0) { rv[warp] = bv; rj[warp] = bj; rs[warp] = bs; rc[warp] = bc; }
         __syncthreads();
-        // every warp reduces the 32 warp results redundantly: all threads know the CTA's candidate without another barrier
-        bv = rv[lane]; bj = rj[lane]; bs = rs[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oj = __shfl_xor_sync(0xffffffffu, bj, o), os = __shfl_xor_sync(0xffffffffu, bs, o);
-            if (ov < bv || (ov == bv && ov < 1.7976931348623157e308 && oj < bj)) { bv = ov; bj = oj; bs = os; }
-        }
-        // the owner thread of the CTA's candidate publishes its core distance
-        const bool have = bv < 1.7976931348623157e308;
-        const int loc = bj - base;
-        if (have && (loc & (HDB_PRIM_THREADS - 1)) == tid) {
-            const int q = loc >> 10;
-            double c = 0.0;
-#pragma unroll
-            for (int qq = 0; qq < HDB_PT_MAX; ++qq) if (qq == q) c = crj[qq];
-            s_cd = c;
-        }
-        __syncthreads();
-        // lanes 0..HDB_CS-1 of warp 0 store the candidate record into the peers' shared memory (double buffered by step parity)
-        if (warp == 0 && lane < HDB_CS) {
-            HdbCand rec;
-            rec.v = bv; rec.j = bj; rec.s = bs; rec.pad = 0.0;
-            rec.x = have ? xs[loc] : make_double4(0, 0, 0, 0);
-            rec.cd = have ? s_cd : 0.0;
-            HdbCand* peer = cluster.map_shared_rank(recs, lane);
-            peer[(i & 1) * HDB_CS + crank] = rec;
+        if (warp == 0) {
+            // second level over the NW warp results, then lanes 0..HDB_CS-1 store the CTA's record into the peers' shared memory
+            bv = lane < NW ? rv[lane] : 1.7976931348623157e308;
+            bj = lane < NW ? rj[lane] : 0x7ffffffe;
+            bs = lane < NW ? rs[lane] : 0;
+            bc = lane < NW ? rc[lane] : 0.0;
+            hdb_warp_argmin(bv, bj, bs, bc);
+            if (lane < HDB_CS) {
+                const bool have = bv < 1.7976931348623157e308;
+                HdbCand rec;
+                rec.v = bv; rec.j = bj; rec.s = bs; rec.pad = 0.0;
+                rec.x = have ? xs[bj - base] : make_double4(0, 0, 0, 0);
+                rec.cd = bc;
+                HdbCand* peer = cluster.map_shared_rank(recs, lane);
+                peer[(i & 1) * HDB_CS + crank] = rec;          // double buffered by step parity
+            }
         }
         cluster.sync();
         // winner of the HDB_CS candidates (lexicographic, like the in-CTA reduction); every thread of every CTA computes it
         const HdbCand* rr = recs + (i & 1) * HDB_CS;
-        double wv = rr[0].v; int wj = rr[0].j, wsrc = rr[0].s, wr = 0;
+        double wv = rr[0].v; int wj = rr[0].j, wr = 0;
 #pragma unroll
         for (int r = 1; r < HDB_CS; ++r) {
             const double ov = rr[r].v; const int oj = rr[r].j;
-            if (ov < wv || (ov == wv && ov < 1.7976931348623157e308 && oj < wj)) { wv = ov; wj = oj; wsrc = rr[r].s; wr = r; }
+            if (ov < wv || (ov == wv && oj < wj)) { wv = ov; wj = oj; wr = r; }
         }
         xc = rr[wr].x; cd = rr[wr].cd; cur = wj;
         if (crank == 0 && tid == 0) {
-            mst_src[(long long)f * (n - 1) + i] = wsrc;
+            mst_src[(long long)f * (n - 1) + i] = rr[wr].s;
             mst_dst[(long long)f * (n - 1) + i] = wj;
             mst_w[(long long)f * (n - 1) + i] = wv;
         }
         const int wl = wj - base;
-        if (wl >= 0 && wl < per_cta && (wl & (HDB_PRIM_THREADS - 1)) == tid) live &= ~(1u << (wl >> 10));
+        if (wl >= 0 && wl < per_cta && (wl & (HDB_CT - 1)) == tid) live &= ~(1u << (wl / HDB_CT));
     }
     cluster.sync();          // no CTA may exit while a peer can still store into its shared memory
 }

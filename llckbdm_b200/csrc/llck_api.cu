@@ -484,13 +484,13 @@ int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32
     if (n < 2 || n > HDB_PRIM_THREADS * 128 || nfits < 1) return LLCK_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     // one thread-block cluster per fit with the points resident in shared memory / registers, when they fit
-    const int pt = (n + HDB_CS * HDB_PRIM_THREADS - 1) / (HDB_CS * HDB_PRIM_THREADS);
+    const int pt = (n + HDB_CS * HDB_CT - 1) / (HDB_CS * HDB_CT);
     if (pt <= HDB_PT_MAX && !(flags & LLCK_MST_SINGLE_CTA)) {
-        const size_t smem = (size_t)pt * HDB_PRIM_THREADS * sizeof(double4) + 2 * HDB_CS * sizeof(HdbCand);
+        const size_t smem = (size_t)pt * HDB_CT * sizeof(double4) + 2 * HDB_CS * sizeof(HdbCand);
         if (cudaFuncSetAttribute(hdb_prim_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
             cudaLaunchConfig_t cfg = {};
             cudaLaunchAttribute attr[1];
-            cfg.blockDim = dim3(HDB_PRIM_THREADS); cfg.dynamicSmemBytes = smem; cfg.gridDim = dim3(nfits * HDB_CS); cfg.stream = st;
+            cfg.blockDim = dim3(HDB_CT); cfg.dynamicSmemBytes = smem; cfg.gridDim = dim3(nfits * HDB_CS); cfg.stream = st;
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = HDB_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;

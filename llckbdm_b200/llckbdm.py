@@ -27,8 +27,8 @@ import attr
 import numpy as np
 
 from . import _native
-from .ensemble import (hdbscan_msts_device, score_rmse_device, silhouette_samples_device, solve_pooled, to_device_complex,
-                       _require_cuda)
+from .ensemble import (group_labels, hdbscan_msts_device, score_rmse_device, silhouette_samples_device, solve_pooled,
+                       to_device_complex, _require_cuda)
 from .kbdm import check_finite, raise_for_status, resolve_m_l
 from .metrics import calculate_freq_domain_rmse  # noqa: F401
 from .min_rmse_kbdm import min_rmse_kbdm  # noqa: F401
@@ -297,29 +297,36 @@ def _fit_all(features, min_samples_list):
 
 def _results_from_labelings(samples, features, labelings):
     """ClusteringResult per labeling with >= 1 cluster (reference llckbdm.py:285-321), silhouettes from one device launch.
-    Clusters are grouped by one stable sort per labeling instead of one ``labels == k`` scan per cluster."""
+    The points are grouped by label ONCE per labeling (``ensemble.group_labels``, a radix sort); the grouping feeds the
+    silhouette kernel and replaces the reference's one ``labels == k`` scan per cluster."""
     keep = [np.asarray(lab) for lab in labelings if np.asarray(lab).max(initial=-1) >= 0]
     if not keep:
         return []
-    sil_all = silhouette_samples_device(features, keep)
+    groups = [group_labels(lab) for lab in keep]
+    sil_all = silhouette_samples_device(features, keep, groups=groups)
     rates = samples.copy()
     rates[:, 1] = 1 / rates[:, 1]                      # T2 is averaged as a rate (reference llckbdm.py:345-349)
     results = []
-    for labels, sil in zip(keep, sil_all):
+    for labels, sil, (order, _cof, seg, values) in zip(keep, sil_all, groups):
         num_clusters = int(labels.max()) + 1             # HDBSCAN labels are 0..k-1 (+ -1 for noise)
-        order = np.argsort(labels, kind="stable")        # ascending indices inside every cluster == np.nonzero(labels == k)
-        bounds = np.searchsorted(labels[order], np.arange(num_clusters + 1))
+        order = order.astype(np.intp)                    # ascending indices inside every group == np.nonzero(labels == k)
+        first = int(np.searchsorted(values, 0))          # groups below are negative labels (noise)
+        contiguous = len(values) - first == num_clusters
+        if contiguous:
+            bounds = seg[first:first + num_clusters + 1].astype(np.intp)
+        else:                                            # label values with gaps: not produced by HDBSCAN
+            bounds = np.searchsorted(labels[order], np.arange(num_clusters + 1))
         starts, counts = bounds[:-1], np.diff(bounds)
         clustered = [(order[bounds[k]:bounds[k + 1]],) for k in range(num_clusters)]
         if np.all(counts > 0):
             cluster_sil = np.add.reduceat(sil[order], starts) / counts
             summary = np.add.reduceat(rates[order], starts, axis=0) / counts[:, None]
             summary[:, 1] = 1 / summary[:, 1]
-        else:                                            # not produced by HDBSCAN; keep the reference's per-cluster semantics
+        else:                                            # keep the reference's per-cluster semantics
             cluster_sil = np.array([np.average(sil[c]) for c in clustered])
             summary = _summarize_clusters(samples=samples, clusters=clustered)
-        results.append(ClusteringResult(num_clusters=num_clusters, labels=labels, clustered=clustered,
-                                        non_clustered=np.nonzero(labels == -1),
+        noise = order[:seg[first]] if first > 0 and values[0] == -1 and first == 1 else np.nonzero(labels == -1)[0]
+        results.append(ClusteringResult(num_clusters=num_clusters, labels=labels, clustered=clustered, non_clustered=(noise,),
                                         summarized_line_list=summary, clustered_silhouettes=np.asarray(cluster_sil)))
     return results
 

@@ -148,6 +148,19 @@ def test_plan_chunks_whole_waves():
     assert plan_chunks(0, 10) == []
 
 
+def test_group_labels_equals_unique_plus_stable_argsort():
+    from llckbdm_b200.ensemble import group_labels
+    rng = np.random.default_rng(0)
+    cases = [rng.integers(-1, 30, 1000), rng.integers(0, 5, 100), np.array([5, 5, 9, -1, 9, 100000]), np.arange(10) // 3 * 7 - 1,
+             np.zeros(5, dtype=int), np.array([-1, -1, 2, 2, 0, 1])]
+    for lab in cases:
+        order, cluster_of, seg, values = group_labels(lab)
+        uniq, inv = np.unique(lab, return_inverse=True)
+        want = np.argsort(inv, kind="stable")
+        assert np.array_equal(order, want) and np.array_equal(cluster_of, inv[want]) and np.array_equal(values, uniq)
+        assert seg[0] == 0 and np.array_equal(seg[1:], np.cumsum(np.bincount(inv)))
+
+
 def test_flatten_signals():
     a = np.arange(4) + 0j
     flat, off, lens = flatten_signals(a, 3)
