@@ -647,7 +647,7 @@ __global__ void bdc_sv_kernel(BdcParams p, double* sing_vals, long long sv_strid
 
 __global__ void __launch_bounds__(128) bdc_gather_kernel(BdcParams p, const int* lv, const double* sing_vals, long long sv_stride, double q,
                                                          cplx* Lpre, cplx* Rpre, long long cstride, int ldc, int* status,
-                                                         int* fallback, int scale_mode) {
+                                                         const int* fallback, int* imbalance, int scale_mode) {
     const int b = blockIdx.y, k = blockIdx.x;
     const int m = p.mv[b], l = scale_mode ? m : lv[b];
     if (k >= l || fallback[b]) return;
@@ -664,8 +664,9 @@ __global__ void __launch_bounds__(128) bdc_gather_kernel(BdcParams p, const int*
     __syncthreads();
     nv = block_sum(nv, red);
     // safety net: an eigenvector (v1,u1,v2,u2,...)/sqrt2 of the Golub-Kahan matrix has |u|^2 = |v|^2 = 1/2; a visible imbalance means the
-    // +sigma/-sigma pair was not separated -> hand the member to the Jacobi path (read by the fallback count that follows this kernel)
-    if (threadIdx.x == 0 && !scale_mode && !(fabs(nu - 0.5) < 1e-5 && fabs(nv - 0.5) < 1e-5)) atomicExch(&fallback[b], 1);
+    // +sigma/-sigma pair was not separated -> hand the member to the Jacobi path.  The flag goes to a separate array (merged into
+    // fallback[] by the kernel that follows), so no block of this kernel reads a word a sibling block is writing.
+    if (threadIdx.x == 0 && !scale_mode && !(fabs(nu - 0.5) < 1e-5 && fabs(nv - 0.5) < 1e-5)) atomicExch(&imbalance[b], 1);
     const double s = sing_vals[(long long)b * sv_stride + k];
     double fu = rsqrt(nu), fv = rsqrt(nv);
     if (scale_mode) fu *= s;

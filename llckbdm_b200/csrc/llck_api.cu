@@ -68,9 +68,12 @@ __global__ void mark_unconverged_kernel(const int* done, int* status, int batch)
 }
 
 // members flagged by the divide-and-conquer SVD are the only ones the Jacobi path still has to solve
-__global__ void fallback_to_done_kernel(const int* fallback, int* done, int batch) {
+__global__ void fallback_to_done_kernel(int* fallback, const int* imbalance, int* done, int batch) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < batch) done[b] = fallback[b] ? 0 : 1;
+    if (b >= batch) return;
+    const int fb = (fallback[b] | imbalance[b]) ? 1 : 0;      // rank-deficiency test of bdc_sv_kernel | u/v imbalance seen by bdc_gather_kernel
+    fallback[b] = fb;
+    done[b] = fb ? 0 : 1;
 }
 
 // loop condition of the Jacobi sweeps (CUDA graph WHILE node): another sweep iff some member is not converged and sweeps are left.
@@ -91,15 +94,15 @@ __global__ void jacobi_cond_kernel(cudaGraphConditionalHandle handle, const int*
 }
 
 // per-call device state: convergence flags, outputs that are accumulated with atomics
-__global__ void meta_zero_kernel(int* done, unsigned long long* sweep_off, int* status, int* n_valid, int* hqr_sweeps, int batch) {
+__global__ void meta_zero_kernel(int* done, unsigned long long* sweep_off, int* status, int* n_valid, int* hqr_sweeps, int* imbalance, int batch) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
-    done[b] = 0; sweep_off[b] = 0ull; status[b] = 0; n_valid[b] = 0; hqr_sweeps[b] = 0;
+    done[b] = 0; sweep_off[b] = 0ull; status[b] = 0; n_valid[b] = 0; hqr_sweeps[b] = 0; imbalance[b] = 0;
 }
 
 // ---- workspace layout -----------------------------------------------------------------------------
 struct WsLayout {
-    size_t mv, lv, nbv, done, scalars, hqr_sweeps, perm, sig_off, sweep_off, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, bdcvec, fallback, ypart, mats, total;
+    size_t mv, lv, nbv, done, scalars, imbalance, hqr_sweeps, perm, sig_off, sweep_off, vp, yp, vtp, wp, tws, pan6, pan7, dws, ews, jws, gws, offws, skip, bdcvec, fallback, ypart, mats, total;
     int nmats;
 };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -111,6 +114,7 @@ static WsLayout ws_layout(int batch, int ld, int flags) {
     L.nbv = o; o = al256(o + sizeof(int) * batch);
     L.done = o; o = al256(o + sizeof(int) * batch);
     L.scalars = o; o = al256(o + 256);
+    L.imbalance = o; o = al256(o + sizeof(int) * batch);
     L.hqr_sweeps = o; o = al256(o + sizeof(int) * batch);
     L.perm = o; o = al256(o + sizeof(int) * (size_t)batch * ld);
     L.sig_off = o; o = al256(o + sizeof(long long) * batch);
@@ -542,7 +546,7 @@ int llck_bdc_test(const double* d, const double* e, const int32_t* m, int32_t ba
     const size_t qbytes = sizeof(double) * (size_t)batch * 4 * ld * ld;
     const size_t vbytes = bdc_vec_bytes(batch, 2 * ld);
     unsigned char* w = nullptr;
-    CK(cudaMalloc(&w, 2 * qbytes + qbytes / 2 + vbytes + 2 * sizeof(int) * (size_t)batch + 1024));
+    CK(cudaMalloc(&w, 2 * qbytes + qbytes / 2 + vbytes + 3 * sizeof(int) * (size_t)batch + 1024));
     BdcParams bp;
     bp.dws = d; bp.ews = e; bp.ld = ld; bp.batch = batch; bp.ldq = 2 * ld;
     bp.qstride = 4LL * ld * ld; bp.xstride = 2LL * ld * ld;
@@ -550,14 +554,15 @@ int llck_bdc_test(const double* d, const double* e, const int32_t* m, int32_t ba
     bdc_carve_vectors(bp, w + 2 * qbytes + qbytes / 2, batch, 2 * ld);
     int* d_m = (int*)(w + 2 * qbytes + qbytes / 2 + vbytes);
     int* d_status = d_m + batch;
+    int* d_imb = d_status + batch;
     bp.mv = d_m; bp.level = 0;
     cudaError_t e1 = cudaMemcpyAsync(d_m, m, sizeof(int) * batch, cudaMemcpyHostToDevice, st);
-    if (e1 == cudaSuccess) e1 = cudaMemsetAsync(d_status, 0, sizeof(int) * batch, st);
+    if (e1 == cudaSuccess) e1 = cudaMemsetAsync(d_status, 0, 2 * sizeof(int) * batch, st);
     int rc = (e1 == cudaSuccess) ? bdc_driver(bp, mmax, st) : -(int)e1;
     if (rc == 0) {
         bdc_sv_kernel<<<batch, 256, 0, st>>>(bp, sing_vals, ld, fallback);
         dim3 grid(mmax, batch);
-        bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_m, sing_vals, ld, 0.0, (cplx*)Us, (cplx*)V, (long long)ld * ld, ld, d_status, fallback, 1);
+        bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_m, sing_vals, ld, 0.0, (cplx*)Us, (cplx*)V, (long long)ld * ld, ld, d_status, fallback, d_imb, 1);
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) rc = -(int)e2;
     }
@@ -653,7 +658,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
         CK(cudaMemcpyAsync(d_nbv, h, sizeof(int) * batch, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_soff, sig_offset, sizeof(long long) * batch, cudaMemcpyHostToDevice, st));
     }
-    meta_zero_kernel<<<(batch + 255) / 256, 256, 0, st>>>(d_done, d_swoff, status, n_valid, d_hqrs, batch);
+    meta_zero_kernel<<<(batch + 255) / 256, 256, 0, st>>>(d_done, d_swoff, status, n_valid, d_hqrs, (int*)(ws + L.imbalance), batch);
     LLCK_LAUNCHED();
     CK(cudaGetLastError());
 
@@ -701,9 +706,9 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
             bdc_sv_kernel<<<batch, 256, 0, st>>>(bp, sing_vals, sv_stride, d_fallback);
             LLCK_LAUNCHED();
             dim3 grid(lmax, batch);
-            bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_lv, sing_vals, sv_stride, q, bLpre, bRpre, stride, ld, status, d_fallback, 0);
+            bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_lv, sing_vals, sv_stride, q, bLpre, bRpre, stride, ld, status, d_fallback, (int*)(ws + L.imbalance), 0);
             LLCK_LAUNCHED();
-            fallback_to_done_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_fallback, d_done, batch);
+            fallback_to_done_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_fallback, (const int*)(ws + L.imbalance), d_done, batch);
             LLCK_LAUNCHED();
             CK(cudaGetLastError());
         }
@@ -767,7 +772,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
             CK(cudaMemsetAsync(mat(1), 0, sizeof(cplx) * batch * stride, st));
             dim3 grid(mmax, batch);
             rsvd_gather_kernel<<<grid, 128, 0, st>>>(Xr, Vr, rstride, ld, d_mv, d_lv, sing_vals, sv_stride, d_perm, q, bLpre, bRpre, stride, status, 1, d_only);
-            if (use_dc) bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_lv, sing_vals, sv_stride, q, bLpre, bRpre, stride, ld, status, d_fallback, 1);
+            if (use_dc) bdc_gather_kernel<<<grid, 128, 0, st>>>(bp, d_lv, sing_vals, sv_stride, q, bLpre, bRpre, stride, ld, status, d_fallback, (int*)(ws + L.imbalance), 1);
             CK(cudaGetLastError());
             g.A = bQ; g.B = bLpre; g.C = mat(0); g.Nv = d_mv;
             CK(zgemm_batched(A_NORMAL, g, mmax, mmax, mmax, batch, st));

@@ -44,16 +44,18 @@ def main():
     lib = _native.load()
     sigs = [brain_sim(max(2048, 2 * max(ms) + 8), sigma, seed=i) for i in range(len(ms))]
     ls = [m if lsel < 0 else min(lsel, m) for m in ms]
-    flat, offs = ensemble.flatten_signals(sigs, len(ms))
+    flat, offs, lens = ensemble.flatten_signals(sigs, len(ms))
     dev = torch.device("cuda:0")
     sig_dev = torch.from_numpy(flat.view(np.float64)).to(dev).view(torch.complex128)
     torch.cuda.synchronize()
     t0 = time.time()
-    r = ensemble.solve_device(sig_dev, offs, ms, ls, p, q, dwell, flags=_native.FLAG_DEBUG_KEEP)
+    ws_bytes = lib.llck_workspace_bytes(len(ms), lib.llck_leading_dim(max(ms)), _native.FLAG_DEBUG_KEEP)
+    ws_dbg = torch.empty(ws_bytes, dtype=torch.uint8, device=sig_dev.device)
+    r = ensemble.solve_device(sig_dev, offs, ms, ls, p, q, dwell, flags=_native.FLAG_DEBUG_KEEP, workspace=ws_dbg, sig_len=lens)
     torch.cuda.synchronize()
     print(f"solve time {time.time() - t0:.3f}s info={r['info']} status={r['status'].cpu().tolist()} n_valid={r['n_valid'].cpu().tolist()}")
     ld = r["ld"]
-    M = get_mats(r["workspace"], lib, len(ms), ld)
+    M = get_mats(ws_dbg, lib, len(ms), ld)
     sv = r["sing_vals"].cpu().numpy()
     ll = r["line_lists"].cpu().numpy()
     mu = r["mu"].cpu().numpy()
