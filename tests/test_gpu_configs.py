@@ -446,3 +446,36 @@ def test_jacobi_fallback_runs_as_device_side_while_graph(cuda):
             assert len(est) == 16
             assert np.allclose(est[:, 0], BRAIN_SIM_PARAMS[:, 0], rtol=1e-6) and np.allclose(est[:, 2], BRAIN_SIM_PARAMS[:, 2], atol=1e-6)
     assert np.allclose(a.sing_vals[1, :16], b.sing_vals[1, :16], rtol=1e-10)
+
+
+def test_pooled_path_in_several_chunks_keeps_member_order(cuda):
+    """solve_pooled with the ensemble split into cost-sorted chunks (as the scheduler does for ensembles larger than the HBM or
+    with a wave remainder): the pooled rows must still come in m_range order and equal the one-chunk result bit for bit per member."""
+    from llckbdm_b200.ensemble import solve_pooled
+    from oracle.kbdm_oracle import brain_sim
+    c = brain_sim(1024, 1e-3, 9)
+    ms = [40, 300, 64, 129, 17, 200, 33]
+    s1, f1, st1 = solve_pooled(c, ms, ms, 1, 0.0, DWELL)
+    s3, f3, st3 = solve_pooled(c, ms, ms, 1, 0.0, DWELL, chunk=3)
+    assert (st1 == 0).all() and (st3 == 0).all()
+    assert s1.shape == s3.shape and f1.shape == f3.shape
+    # chunks are other batches (other thread-block cluster sizes): compare per member, well-conditioned rows, to parity tolerance
+    big1, big3 = s1[:, 0] > 1e-3 * s1[:, 0].max(), s3[:, 0] > 1e-3 * s3[:, 0].max()
+    assert np.array_equal(big1, big3)
+    assert np.allclose(s1[big1][:, [0, 2]], s3[big3][:, [0, 2]], rtol=1e-8, atol=1e-10)
+    assert np.allclose(f1[big1], f3[big3], rtol=1e-8, atol=1e-10)
+
+
+def test_kbdm_p2_q_truncated_at_c2_size(cuda):
+    """Shift p = 2, Tikhonov q > 0 and l < m at a config-C2 size (m = 700, l = 200) against the oracle: the options of
+    reference kbdm.py:19 are not only exercised at toy sizes."""
+    from llckbdm_b200.ensemble import solve_ensemble
+    from oracle.kbdm_oracle import brain_sim, compare_members, kbdm_oracle
+    c = brain_sim(2048, 1e-3, 0)
+    res = solve_ensemble(c, [700, 700], [200, 700], 2, 1e-3, DWELL)
+    assert (res.status == 0).all()
+    for k, l in enumerate((200, 700)):
+        _, info, mu, D = kbdm_oracle(c, DWELL, m=700, l=l, p=2, q=1e-3, return_mu=True)
+        dmu, dD = compare_members(res.mu[k, :l], res.D[k, :l], mu, D)
+        assert dmu < TOL and dD < TOL, (l, dmu, dD)
+        assert np.allclose(res.sing_vals[k, :700], info.singular_values, rtol=1e-8, atol=1e-12)
