@@ -14,7 +14,10 @@
 #define BD_NB 32
 
 // dynamic smem: (2*ld + 2*BD_NB*BD_NB + 8*BD_NB + 8) * 16 + 512
-__global__ void __launch_bounds__(E_THREADS, 1) bidiag_panel_kernel(cplx* A, long long stride, int ld, const int* mv, int k0,
+// MINB = 2: two CTAs (members) per SM for batches of more than one wave -- one member's serial vector phase overlaps the other's
+// streaming gemv pass (64 registers per thread, a few spilled words); MINB = 1 for single-wave batches and cluster launches.
+template <int MINB>
+__global__ void __launch_bounds__(E_THREADS, MINB) bidiag_panel_kernel(cplx* A, long long stride, int ld, const int* mv, int k0,
                                                                     cplx* Vp, cplx* Yp, cplx* Xp, cplx* Up, long long pstride,
                                                                     cplx* TQws, cplx* TPws, long long tstride, double* dws, double* ews,
                                                                     cplx* ypart, int csize) {

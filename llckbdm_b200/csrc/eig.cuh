@@ -44,7 +44,9 @@ __device__ __forceinline__ void cluster_barrier(int csize) {
 // dynamic smem: (2*ld + HB_NB*HB_NB + 4*HB_NB) * 16 + 512
 // ---------------------------------------------------------------------------------------------
 #define HB_NB 32
-__global__ void __launch_bounds__(E_THREADS, 1) hess_panel_kernel(cplx* H, long long stride, int ld, const int* lv, int k0,
+// MINB = 2: two CTAs per SM for multi-wave batches (see bidiag_panel_kernel)
+template <int MINB>
+__global__ void __launch_bounds__(E_THREADS, MINB) hess_panel_kernel(cplx* H, long long stride, int ld, const int* lv, int k0,
                                                                   cplx* Vp, cplx* Yp, cplx* VTp, long long pstride,
                                                                   cplx* Tws, long long tstride, cplx* ypart, int csize) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -197,6 +197,14 @@ static cudaError_t launch_clustered(void (*kernel)(KArgs...), int batch, int csi
 }
 
 
+// The level-2 panel kernels are HBM-bound with serial vector phases in between the streaming passes: when the batch is larger than
+// one wave (one CTA per SM), two members per SM keep the memory system busy through those phases (needs 2 x smem <= the SM's 227 KB).
+static bool panels_two_per_sm(int batch, size_t smem) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+    return batch > sms && 2 * (smem + 1024) <= 227 * 1024;
+}
+
 // ---- blocked bidiagonalisation driver (shared by llck_kbdm_batched and the stage test entry) ---------------------
 // A (in: matrices, out: reflectors + d/e), Q and P (out, ld x m each), panel buffers Vp/Yp/Xp/Up (ld x 32 each), Wp (32 x ld),
 // TQws/TPws ((ld/32) x 32 x 32 each), dws/ews (ld doubles each) -- all per member with the given strides.
@@ -208,13 +216,15 @@ static int bidiag_driver(cplx* A, cplx* Q, cplx* P, long long stride, int ld, co
     const long long pstride2 = 2 * pstride;
     cplx* Vp = VX; cplx* Xp = VX + pstride; cplx* Yp = YU; cplx* Up = YU + pstride;
     size_t sm = (size_t)(2 * ld + 2 * BD_NB * BD_NB + 8 * BD_NB + 8) * 16 + 512;
-    CK(cudaFuncSetAttribute(bidiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const int bp_csize = (ypart != nullptr && batch <= 74) ? pick_cluster_size(bidiag_panel_kernel, batch, E_THREADS, sm, LLCK_MAX_CLUSTER, forced_cluster) : 1;
+    CK(cudaFuncSetAttribute(bidiag_panel_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CK(cudaFuncSetAttribute(bidiag_panel_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int bp_csize = (ypart != nullptr && batch <= 74) ? pick_cluster_size(bidiag_panel_kernel<1>, batch, E_THREADS, sm, LLCK_MAX_CLUSTER, forced_cluster) : 1;
+    const bool two_per_sm = panels_two_per_sm(batch, sm);
     int k0_last = 0;
     for (int k0 = 0; k0 < mmax; k0 += BD_NB) {
         k0_last = k0;
-        CK(launch_clustered(bidiag_panel_kernel, batch, bp_csize, E_THREADS, sm, st, A, stride, ld, d_mv, k0, Vp, Yp, Xp, Up, pstride2, TQws, TPws, pstride,
-                            dws, ews, ypart, bp_csize));
+        CK(launch_clustered(two_per_sm ? bidiag_panel_kernel<2> : bidiag_panel_kernel<1>, batch, bp_csize, E_THREADS, sm, st, A, stride, ld, d_mv, k0,
+                            Vp, Yp, Xp, Up, pstride2, TQws, TPws, pstride, dws, ews, ypart, bp_csize));
         const int e = k0 + BD_NB;
         if (e >= mmax) continue;
         GemmParams g = gemm_params_zero();
@@ -806,13 +816,15 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
         cplx* Wp = (cplx*)(ws + L.wp); cplx* Tws = (cplx*)(ws + L.tws);
         const long long pstride = (long long)ld * HB_NB;
         size_t sm = (size_t)(2 * ld + HB_NB * HB_NB + 4 * HB_NB) * 16 + 512;
-        CK(cudaFuncSetAttribute(hess_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        const int hp_csize = (batch <= 74) ? pick_cluster_size(hess_panel_kernel, batch, E_THREADS, sm, LLCK_MAX_CLUSTER, o.cluster_size) : 1;
+        CK(cudaFuncSetAttribute(hess_panel_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CK(cudaFuncSetAttribute(hess_panel_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        const int hp_csize = (batch <= 74) ? pick_cluster_size(hess_panel_kernel<1>, batch, E_THREADS, sm, LLCK_MAX_CLUSTER, o.cluster_size) : 1;
+        const bool hp_two = panels_two_per_sm(batch, sm);
         GemmParams hp = gemm_params_zero();
         int k0_last = 0;
         for (int k0 = 0; k0 + 2 < lmax; k0 += HB_NB) {
             k0_last = k0;
-            CK(launch_clustered(hess_panel_kernel, batch, hp_csize, E_THREADS, sm, st, bH, stride, ld, d_lv, k0, Vp, Yp, VTp, pstride, Tws, pstride,
+            CK(launch_clustered(hp_two ? hess_panel_kernel<2> : hess_panel_kernel<1>, batch, hp_csize, E_THREADS, sm, st, bH, stride, ld, d_lv, k0, Vp, Yp, VTp, pstride, Tws, pstride,
                                 (cplx*)(ws + L.ypart), hp_csize));
             const int e = k0 + HB_NB;
             const int r0 = k0 + 1;
