@@ -11,7 +11,7 @@ backend (CPU tensors) is used by the CPU tests, which inject a solver stub.
 """
 import numpy as np
 
-from .ensemble import flops_per_solve, lpt_shards, solve_chunks, flatten_signals, to_device_complex
+from .ensemble import flops_per_solve, lpt_shards, solve_chunks, to_device_complex
 
 
 def record_bytes(lmax, mmax):
@@ -19,14 +19,19 @@ def record_bytes(lmax, mmax):
     return 8 * (4 * lmax + mmax) + 8
 
 
-def shard_signals(flat, offsets, lens, mine, shared):
-    """The part of the FID buffer a rank has to upload: the one shared FID, or only its own members' FIDs re-packed."""
-    if shared or len(mine) == 0:
-        return flat if shared else flat[:0], offsets[mine], lens[mine]
-    parts = [flat[offsets[i]:offsets[i] + lens[i]] for i in mine]
-    new_len = lens[mine]
-    new_off = np.concatenate(([0], np.cumsum(new_len)[:-1])).astype(np.int64)
-    return np.concatenate(parts), new_off, new_len
+def shard_signals(signals, M, mine):
+    """The FIDs a rank has to upload -> (flat complex128 array, offsets, lengths of ITS members): the one shared FID, or only its own
+    members' FIDs packed back to back (the other members' signals are never touched)."""
+    if isinstance(signals, np.ndarray) and signals.ndim == 1:
+        flat = np.ascontiguousarray(signals, dtype=np.complex128)
+        return flat, np.zeros(len(mine), dtype=np.int64), np.full(len(mine), flat.size, dtype=np.int64)
+    if len(signals) != M:
+        raise ValueError("need one signal per member")
+    parts = [np.ascontiguousarray(signals[i], dtype=np.complex128).ravel() for i in mine]
+    lens = np.array([len(x) for x in parts], dtype=np.int64)
+    offs = (np.concatenate(([0], np.cumsum(lens)[:-1])) if len(parts) else np.zeros(0)).astype(np.int64)
+    flat = np.concatenate(parts) if parts else np.zeros(0, dtype=np.complex128)
+    return flat, offs, lens
 
 
 def _pack_into(buf, rows, r, lmax, mmax, torch):
@@ -121,9 +126,7 @@ def solve_ensemble_distributed(signals, m, l, p, q, dwell, group=None, local_sol
     """
     import torch
     plan = plan_shards(m, l, group)
-    flat, offsets, lens = flatten_signals(signals, plan.M)
-    shared = isinstance(signals, np.ndarray) and signals.ndim == 1
-    my_flat, my_off, my_len = shard_signals(flat, offsets, lens, plan.mine, shared)
+    my_flat, my_off, my_len = shard_signals(signals, plan.M, plan.mine)
     if local_solver is None:
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         with torch.cuda.device(dev):
