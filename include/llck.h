@@ -106,7 +106,8 @@ size_t llck_debug_offset(int batch, int ld, int which);
  *   n_valid    [dev]  int32   [batch]              rows passing filter_samples (A>1e-6 and T2>0, sampling.py:92-95)
  *   status     [dev]  int32   [batch]              LLCK_STATUS_*
  *   opts       [host] llck_options (optional, NULL = defaults)
- *   info       [host] int32   [16] (optional)      [2]=ld, [3]=Jacobi column blocks of the largest member, [13]=kernels enqueued by
+ *   info       [host] int32   [16] (optional)      [0]=host microseconds spent building and launching the Jacobi loop graph, [2]=ld,
+ *                                                  [3]=Jacobi column blocks of the largest member, [13]=kernels enqueued by
  *                                                  this call (counted at the launch sites; a graph launch counts once),
  *                                                  [14]=1 if the Jacobi sweeps ran as a device-side WHILE graph node; with
  *                                                  LLCK_FLAG_TIMING also [1]=max QR multishift sweeps and [4..12]=stage durations in us

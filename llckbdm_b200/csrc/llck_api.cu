@@ -968,7 +968,7 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
         for (int i = 0; i < 16; ++i) info[i] = 0;
         info[2] = ld; info[3] = nbmax;
         info[13] = llck_launch_count;                 // kernels enqueued by this call, counted at the launch sites
-        info[0] = graph_us[0]; info[5] = graph_us[1]; info[6] = graph_us[2]; info[7] = graph_us[3];
+        info[0] = graph_us[0] + graph_us[1] + graph_us[2] + graph_us[3];      // host microseconds spent building / launching the Jacobi loop graph
         info[14] = jacobi_graph;                      // 1: the Jacobi sweeps ran as a device-side WHILE graph node, 0: enqueued unconditionally
     }
     if (timing) {

@@ -365,6 +365,11 @@ def test_solve_call_is_asynchronous_and_stream_ordered(cuda):
         dmu, dD = compare_members(r["mu"][k, :m].cpu().numpy(), r["D"][k, :m].cpu().numpy(), mu, D)
         assert dmu < TOL and dD < TOL
     assert r["info"][13] > 0 and r["info"][2] == 448 and r["info"][14] == 1
+    # the cached workspace and the parked graphs can be released and come back on demand
+    ensemble.release_workspace()
+    r = ensemble.solve_device(sig, zeros[:3], ms[:3], ms[:3], 1, 0.0, DWELL)
+    torch.cuda.synchronize()
+    assert int(r["status"].abs().sum().item()) == 0
 
 
 def test_short_signal_is_an_error_not_an_out_of_bounds_read(cuda):
