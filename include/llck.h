@@ -69,8 +69,8 @@ typedef struct llck_options {
     int32_t struct_size;
     int32_t svd_mode;            /* LLCK_SVD_* */
     int32_t cluster_size;        /* CTAs per member of the one-CTA-per-member kernels for batches <= 74: 0 = auto, else 1, 2, 4 or 8 */
-    int32_t aed_window;          /* aggressive-early-deflation window of the multishift QR, 8..48; 0 = default (24) */
-    int32_t aed_nibble;          /* percent of the window that must deflate to skip the sweep (LAPACK NIBBLE); 0 = adaptive */
+    int32_t aed_window;          /* aggressive-early-deflation window of the multishift QR, 8..48; 0 = default (32 above l = 640, else 28) */
+    int32_t aed_nibble;          /* percent of the window that must deflate to skip the sweep (LAPACK NIBBLE); 0 = default (60) */
     int32_t jacobi_max_sweeps;   /* sweeps enqueued for the Jacobi SVD (converged members exit at once); 0 = default (30) */
     double  jacobi_conv;         /* scaled off-diagonal threshold that ends a member's Jacobi iteration; 0 = default (1e-6) */
     void*   hqr_profile;         /* [dev] int64 [batch][10], optional: clock64 phase split of hqr_kernel per member (profiling) */

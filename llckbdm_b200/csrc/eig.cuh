@@ -362,7 +362,7 @@ __device__ __noinline__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, 
 //      ns x ns block to Hessenberg form (transformations accumulated in V); the caller writes T back and applies V.
 // Returns ns (>= 0), or -1 if the window QR failed.  out[0] = 1 if T/V must be written back.  newsub = new H[kwtop,kwtop-1].
 // ---------------------------------------------------------------------------------------------
-#define E_NW 24        // AED window (measured at m=1024: 16 -> 1280, 24 -> 1135, 32 -> 1188, 40 -> 1397 Mcycles per member)
+// AED window: chosen by the host driver (28 up to l = 640, 32 above; llck_options.aed_window overrides), at most 48 (vbuf / shifts hold 64)
 __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shifts, cplx* vbuf, int* out, cplx* newsub, long long* ap) {
     const int lane = threadIdx.x & 31;
     const int L = E_LDH, LV = E_LDW;       // T lives in Hw (ld E_LDH), V in Ww (ld E_LDW)
@@ -744,9 +744,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
             PROF(8);
             if (nd > 0) { ihi -= nd; its = 0; }
             // good deflation: look again before sweeping.  A sweep costs O(n^2), the single-warp AED a constant, so the threshold
-            // (LAPACK's NIBBLE) grows for small matrices: measured hqr ms at nibble 14/30/60: n=1024 586/583/746, n=512 1024/972/918,
-            // n=256 635/585/504
-            const int nib = nibble > 0 ? nibble : (n > 768 ? 30 : 60);
+            // (LAPACK's NIBBLE) is high: round 1 (window 24) measured hqr ms at nibble 14/30/60: n=512 1024/972/918, n=256 635/585/504;
+            // with the round-2 windows (28 / 32) every nibble in 45..100 gives the same time at n = 768 and 1024 and beats 30
+            const int nib = nibble > 0 ? nibble : 60;
             if (nd * 100 > nib * nw || ihi - ilo + 1 <= E_W) continue;
             if (ns < 2 || (its > 0 && its % 6 == 0)) {
                 __syncthreads();
