@@ -69,7 +69,7 @@ typedef struct llck_options {
     int32_t struct_size;
     int32_t svd_mode;            /* LLCK_SVD_* */
     int32_t cluster_size;        /* CTAs per member of the one-CTA-per-member kernels for batches <= 74: 0 = auto, else 1, 2, 4 or 8 */
-    int32_t aed_window;          /* aggressive-early-deflation window of the multishift QR, 8..48; 0 = default (32 above l = 640, else 28) */
+    int32_t aed_window;          /* aggressive-early-deflation window of the multishift QR, 8..48; 0 = default (24 / 28 / 32 for l <= 448 / <= 704 / larger) */
     int32_t aed_nibble;          /* percent of the window that must deflate to skip the sweep (LAPACK NIBBLE); 0 = default (60) */
     int32_t jacobi_max_sweeps;   /* sweeps enqueued for the Jacobi SVD (converged members exit at once); 0 = default (30) */
     double  jacobi_conv;         /* scaled off-diagonal threshold that ends a member's Jacobi iteration; 0 = default (1e-6) */

@@ -362,7 +362,7 @@ __device__ __noinline__ int warp_small_hqr(cplx* Hs, int ldh, cplx* W, int ldw, 
 //      ns x ns block to Hessenberg form (transformations accumulated in V); the caller writes T back and applies V.
 // Returns ns (>= 0), or -1 if the window QR failed.  out[0] = 1 if T/V must be written back.  newsub = new H[kwtop,kwtop-1].
 // ---------------------------------------------------------------------------------------------
-// AED window: chosen by the host driver (28 up to l = 640, 32 above; llck_options.aed_window overrides), at most 48 (vbuf / shifts hold 64)
+// AED window: chosen by the host driver (24 / 28 / 32 by size; llck_options.aed_window overrides), at most 48 (vbuf / shifts hold 64)
 __device__ __noinline__ int warp_aed(cplx* T, cplx* V, int nw, cplx s, cplx* shifts, cplx* vbuf, int* out, cplx* newsub, long long* ap) {
     const int lane = threadIdx.x & 31;
     const int L = E_LDH, LV = E_LDW;       // T lives in Hw (ld E_LDH), V in Ww (ld E_LDW)
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) hqr_kernel(cplx* H, cplx* Z, lon
         }
         ++its;
         if (its > 60) { failed = true; break; }
-        // ---- aggressive early deflation on the trailing E_NW x E_NW window; its undeflated eigenvalues are the shifts ----
+        // ---- aggressive early deflation on the trailing aed_nw x aed_nw window; its undeflated eigenvalues are the shifts ----
         int nbu = E_NB, ntrains = 1, ns_all = E_NB;
         {
             const int nw = aed_nw;                    // size > E_W >= nw

@@ -906,8 +906,8 @@ int llck_kbdm_batched(const void* signals, const int64_t* sig_offset, const int6
         TICK();   // 5: hessenberg done
         CK(cudaFuncSetAttribute(hqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HQR_SMEM_BYTES));
         // AED window: measured on B200 (tools/aed_sweep.py, hqr ms at window 24 / 28 / 32 with nibble 60): l = 1024: 589 / 576 / 561,
-        // l = 768: 297 / 287 / 282, l = 512: 470 / 466 / 475
-        const int aed_nw = o.aed_window > 0 ? o.aed_window : (lmax > 640 ? 32 : 28);
+        // l = 768: 297 / 287 / 282, l = 640: 388 / 375 / 375, l = 512: 470 / 466 / 475, l = 384: 264 / 267 / 279, l = 256: 260 / 274 / 295
+        const int aed_nw = o.aed_window > 0 ? o.aed_window : (lmax > 704 ? 32 : (lmax > 448 ? 28 : 24));
         // small batches: a thread-block cluster of csize CTAs per member shares the strip GEMMs (the window chase / AED run redundantly in
         // every CTA of the cluster); csize = largest power of two that still gives every cluster its own SMs
         const int csize = (batch <= 74) ? pick_cluster_size(hqr_kernel, batch, E_THREADS, HQR_SMEM_BYTES, LLCK_MAX_CLUSTER, o.cluster_size) : 1;
