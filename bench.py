@@ -254,7 +254,7 @@ def run_native(args):
         buf = distributed.solve_shard_device(plan, my_dev, my_off, my_len, 1, 0.0, DWELL, buf=buf)
         gathered = distributed.gather_records(plan, buf)
     if args.warmup:
-        st = distributed.unpack_records(plan, gathered.cpu().numpy())["status"]
+        st = distributed.unpack_records(plan, distributed.records_to_host(gathered))["status"]
         if int((st != 0).sum()) != 0:
             raise RuntimeError("solver reported non-zero status during warm-up")
 
@@ -273,7 +273,7 @@ def run_native(args):
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = M * args.steps / (ms_total * 1e-3)
-    res = distributed.unpack_records(plan, gathered.cpu().numpy())
+    res = distributed.unpack_records(plan, distributed.records_to_host(gathered))
     bad = int((res["status"] != 0).sum())
     stage_us = np.zeros(9)
     launches, hqr_members = 0, 0

@@ -32,7 +32,7 @@ buf = distributed.solve_shard_device(plan, sig_dev, my_off, my_len, 1, 0.0, 5e-4
 torch.cuda.synchronize()
 t_solve = time.perf_counter() - t0
 gathered = distributed.gather_records(plan, buf)
-res = distributed.unpack_records(plan, gathered.cpu().numpy())
+res = distributed.unpack_records(plan, distributed.records_to_host(gathered))
 if world > 1:
     dist.barrier()
 t_all = time.perf_counter() - t0
