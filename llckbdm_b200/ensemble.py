@@ -137,18 +137,75 @@ def solve_chunks(sig_dev, offsets, lens, m, l, p, q, dwell, chunk=None, want_mu=
     for size in sizes:
         idx = order[c0:c0 + size]
         c0 += size
-        yield idx, solve_device(sig_dev, offsets[idx], m[idx], l[idx], p, q, dwell, flags=flags, want_mu=want_mu,
-                                sig_len=lens[idx], options=options)
+        split = None
+        if options is None or options.cluster_size == 0:
+            split = two_stream_split(m[idx], l[idx], sm_count(dev)) if not (flags & _native.FLAG_TIMING) else None
+        if split is None:
+            yield idx, solve_device(sig_dev, offsets[idx], m[idx], l[idx], p, q, dwell, flags=flags, want_mu=want_mu,
+                                    sig_len=lens[idx], options=options)
+            continue
+        # more than half a wave but less than one, ragged sizes: the largest members get a 2-CTA cluster each on a second stream,
+        # the others one CTA each on the caller's stream -- together one CTA per SM, and the slowest member finishes ~1.6x sooner
+        big, small = idx[split[0]], idx[split[1]]
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            need = lib.llck_workspace_bytes(len(big), lib.llck_leading_dim(int(m[big].max())), flags)
+            r_big = solve_device(sig_dev, offsets[big], m[big], l[big], p, q, dwell, flags=flags, want_mu=want_mu, sig_len=lens[big],
+                                 options=_options_with_cluster(options, 2), stream=side, workspace=get_workspace(need, dev, slot=1))
+        r_small = solve_device(sig_dev, offsets[small], m[small], l[small], p, q, dwell, flags=flags, want_mu=want_mu,
+                               sig_len=lens[small], options=_options_with_cluster(options, 1))
+        main.wait_stream(side)
+        for t in r_big.values():
+            if isinstance(t, torch.Tensor):
+                t.record_stream(main)
+        yield big, r_big
+        yield small, r_small
+
+
+def two_stream_split(m, l, sms):
+    """For one launch sequence of M members with sms/2 < M < sms and ragged sizes: positions (into m) of the k = sms - M largest
+    members, which can have two CTAs each, and of the rest -- or None when that would not shorten the critical path (the
+    one-CTA-per-member kernels take as long as their slowest member; a 2-CTA cluster is ~1.6x faster)."""
+    M = len(m)
+    k = sms - M
+    if M <= sms // 2 or M >= sms or k < 4:
+        return None
+    cost = np.array([flops_per_solve(a, b) for a, b in zip(m, l)])
+    order = np.argsort(-cost, kind="stable")
+    if max(cost[order[0]] / 1.6, cost[order[k]]) > 0.9 * cost[order[0]]:
+        return None
+    return np.sort(order[:k]), np.sort(order[k:])
+
+
+def _options_with_cluster(options, cluster_size):
+    opts = _native.Options() if options is None else _native.Options.from_buffer_copy(options)
+    opts.struct_size = ctypes.sizeof(_native.Options)
+    opts.cluster_size = cluster_size
+    return opts
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    torch = _require_cuda()
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
 
 
 _WORKSPACES = {}
 
 
-def get_workspace(nbytes, dev):
+def get_workspace(nbytes, dev, slot=0):
     """The per-device solver workspace, grown on demand and kept between calls (the workspace of a full chunk is most of the HBM:
-    handing it back to the caching allocator after every call fragments it).  ``release_workspace`` frees it."""
+    handing it back to the caching allocator after every call fragments it).  ``release_workspace`` frees it.  ``slot`` 1 is the
+    second workspace of the two-stream schedule."""
     torch = _require_cuda()
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device()) + ((slot,) if slot else ())
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         _WORKSPACES.pop(key, None)
@@ -169,7 +226,9 @@ def release_workspace(dev=None):
         return
     torch = _require_cuda()
     dev = torch.device(dev)
-    _WORKSPACES.pop((dev.type, dev.index if dev.index is not None else torch.cuda.current_device()), None)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    for k in [k for k in _WORKSPACES if k[:2] == key]:
+        _WORKSPACES.pop(k, None)
 
 
 def solve_device(signals_dev, sig_offset, m, l, p, q, dwell, flags=0, workspace=None, stream=None, want_mu=True,

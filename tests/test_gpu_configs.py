@@ -484,3 +484,25 @@ def test_kbdm_p2_q_truncated_at_c2_size(cuda):
         dmu, dD = compare_members(res.mu[k, :l], res.D[k, :l], mu, D)
         assert dmu < TOL and dD < TOL, (l, dmu, dD)
         assert np.allclose(res.sing_vals[k, :700], info.singular_values, rtol=1e-8, atol=1e-12)
+
+
+def test_two_stream_schedule_for_a_ragged_partial_wave(cuda):
+    """100 ragged members (more than half a wave, less than one): the scheduler runs the 48 largest with a 2-CTA cluster each on a
+    second stream next to the 52 others on the caller's stream.  Same results as the plain one-stream launch sequence (parity
+    tolerance: other cluster sizes, other summation splits) and oracle parity on sampled members of both groups."""
+    from llckbdm_b200 import _native
+    from llckbdm_b200.ensemble import solve_ensemble, two_stream_split
+    from oracle.kbdm_oracle import brain_sim, compare_members, kbdm_oracle
+    c = brain_sim(1024, 1e-3, 21)
+    ms = [60 + 2 * k for k in range(100)]
+    assert two_stream_split(np.array(ms), np.array(ms), 148) is not None
+    a = solve_ensemble(c, ms, ms, 1, 0.0, DWELL)                                              # two streams
+    b = solve_ensemble(c, ms, ms, 1, 0.0, DWELL, options=_native.Options(cluster_size=1))     # explicit cluster size: one stream
+    assert (a.status == 0).all() and (b.status == 0).all() and np.array_equal(a.n_valid, b.n_valid)
+    for k in (0, 30, 51, 52, 77, 99):
+        m = ms[k]
+        _, info, mu, D = kbdm_oracle(c, DWELL, m=m, return_mu=True)
+        for res in (a, b):
+            dmu, dD = compare_members(res.mu[k, :m], res.D[k, :m], mu, D)
+            assert dmu < TOL and dD < TOL, (k, dmu, dD)
+        assert np.allclose(a.sing_vals[k, :m], info.singular_values, rtol=1e-8, atol=1e-12)

@@ -148,6 +148,18 @@ def test_plan_chunks_whole_waves():
     assert plan_chunks(0, 10) == []
 
 
+def test_two_stream_split_only_when_it_shortens_the_critical_path():
+    from llckbdm_b200.ensemble import two_stream_split
+    m = np.array([700 + round(k * 324 / 99) for k in range(100)])          # config C2: 100 ragged members on 148 SMs
+    big, small = two_stream_split(m, m, 148)
+    assert len(big) == 48 and len(small) == 52 and m[big].min() > m[small].max()
+    assert sorted(list(big) + list(small)) == list(range(100))
+    assert two_stream_split(np.full(100, 1024), np.full(100, 1024), 148) is None      # equal sizes: nothing to gain
+    assert two_stream_split(m[:60], m[:60], 148) is None                             # <= half a wave: plain cluster launch
+    assert two_stream_split(np.arange(100, 246), np.arange(100, 246), 148) is None   # 146 members: only 2 spare SMs
+    assert two_stream_split(np.arange(100, 300), np.arange(100, 300), 148) is None   # more than one wave
+
+
 def test_group_labels_equals_unique_plus_stable_argsort():
     from llckbdm_b200.ensemble import group_labels
     rng = np.random.default_rng(0)
