@@ -191,6 +191,8 @@ int llck_pool_features(const double* line_lists, int64_t ll_stride, const int32_
  *                              use one CTA per fit that streams the points from L2.  Both give bit-identical edges.        */
 int llck_hdbscan_core_distances(const double* X, int32_t n, int32_t kmax, double* core, void* stream);
 #define LLCK_MST_SINGLE_CTA 1         /* llck_hdbscan_mst flags: always use the one-CTA-per-fit kernel */
+#define LLCK_MST_DIM3 2               /* the caller guarantees that all points share their 4th coordinate (the LLC-KBDM features do: it is 0):
+                                         the cluster kernel leaves it out of the distances -- bit-identical, fewer FP64 instructions */
 int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32_t* core_row, int32_t nfits,
                      double* min_reach, int32_t* cur_src, int64_t* mst_src, int64_t* mst_dst, double* mst_w, int32_t flags, void* stream);
 

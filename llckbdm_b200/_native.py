@@ -33,6 +33,7 @@ FLAG_DEBUG_KEEP = 1
 FLAG_TIMING = 2
 FLAG_NO_GRAPH = 4
 MST_SINGLE_CTA = 1
+MST_DIM3 = 2
 
 E_BADARG = 1
 E_WORKSPACE = 2

@@ -22,6 +22,16 @@ __device__ __forceinline__ double hdb_rdist(const double4 a, const double4 b) {
     return d;
 }
 
+// the same with the last coordinate left out: bit-identical when all points share it (dw = 0 exactly, d + 0 = d); the LLC-KBDM
+// features are (Re mu, Im mu, A, 0) (reference llckbdm.py:219 zeroes the phase feature), and Prim's inner loop is FP64-issue bound
+__device__ __forceinline__ double hdb_rdist3(const double4 a, const double4 b) {
+    const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    double d = __dmul_rn(dx, dx);
+    d = __dadd_rn(d, __dmul_rn(dy, dy));
+    d = __dadd_rn(d, __dmul_rn(dz, dz));
+    return d;
+}
+
 // core[k-1][i] = distance from point i to its k-th nearest neighbour (itself included), k = 1..K
 __global__ void __launch_bounds__(128) hdb_core_kernel(const double* __restrict__ X, int n, int K, double* __restrict__ core) {
     __shared__ double4 tile[HDB_TILE];
@@ -159,6 +169,7 @@ __device__ __forceinline__ void hdb_warp_argmin(double& bv, int& bj, int& bs, do
     bc = __shfl_sync(0xffffffffu, bc, srcl);
 }
 
+template <bool DIM3>
 __global__ void __launch_bounds__(HDB_CT, 1) hdb_prim_cluster_kernel(const double* __restrict__ X, int n, const double* __restrict__ core,
                                                                      const int* __restrict__ core_row, int pt,
                                                                      long long* __restrict__ mst_src, long long* __restrict__ mst_dst,
@@ -171,6 +182,7 @@ __global__ void __launch_bounds__(HDB_CT, 1) hdb_prim_cluster_kernel(const doubl
     constexpr int NW = HDB_CT / 32;
     __shared__ double rv[NW], rc[NW];
     __shared__ int rj[NW], rs[NW];
+    __shared__ int s_win;
     const int f = blockIdx.x / HDB_CS, crank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* cr = core + (long long)core_row[f] * n;
@@ -204,7 +216,7 @@ __global__ void __launch_bounds__(HDB_CT, 1) hdb_prim_cluster_kernel(const doubl
                 // pipe bound) distance / square root are skipped -- results are unchanged, the margin covers the roundings
                 const double m_old = mr[q], lb = fmax(cd, crj[q]);
                 if (lb < m_old) {
-                    const double d2 = hdb_rdist(xc, xs[tid + HDB_CT * q]);
+                    const double d2 = DIM3 ? hdb_rdist3(xc, xs[tid + HDB_CT * q]) : hdb_rdist(xc, xs[tid + HDB_CT * q]);
                     if (d2 < m_old * m_old * 1.0000000000000009) {
                         const double mrd = fmax(lb, __dsqrt_rn(d2));
                         if (mrd < m_old) { mr[q] = mrd; cs[q] = cur; }
@@ -234,19 +246,22 @@ __global__ void __launch_bounds__(HDB_CT, 1) hdb_prim_cluster_kernel(const doubl
             }
         }
         cluster.sync();
-        // winner of the HDB_CS candidates (lexicographic, like the in-CTA reduction); every thread of every CTA computes it
-        const HdbCand* rr = recs + (i & 1) * HDB_CS;
-        double wv = rr[0].v; int wj = rr[0].j, wr = 0;
-#pragma unroll
-        for (int r = 1; r < HDB_CS; ++r) {
-            const double ov = rr[r].v; const int oj = rr[r].j;
-            if (ov < wv || (ov == wv && oj < wj)) { wv = ov; wj = oj; wr = r; }
+        // winner of the HDB_CS candidates (lexicographic, like the in-CTA reduction): warp 0 picks it, everybody reads the result
+        if (warp == 0) {
+            const HdbCand* rr = recs + (i & 1) * HDB_CS;
+            double wv = lane < HDB_CS ? rr[lane].v : 1.7976931348623157e308, wc = 0.0;
+            int wj = lane < HDB_CS ? rr[lane].j : 0x7ffffffe, wr = lane;
+            hdb_warp_argmin(wv, wj, wr, wc);                  // wr: the winning record (carried like the source index)
+            if (lane == 0) { s_win = wr; }
         }
-        xc = rr[wr].x; cd = rr[wr].cd; cur = wj;
+        __syncthreads();
+        const HdbCand* win = recs + (i & 1) * HDB_CS + s_win;
+        xc = win->x; cd = win->cd; cur = win->j;
+        const int wj = cur;
         if (crank == 0 && tid == 0) {
-            mst_src[(long long)f * (n - 1) + i] = rr[wr].s;
+            mst_src[(long long)f * (n - 1) + i] = win->s;
             mst_dst[(long long)f * (n - 1) + i] = wj;
-            mst_w[(long long)f * (n - 1) + i] = wv;
+            mst_w[(long long)f * (n - 1) + i] = win->v;
         }
         const int wl = wj - base;
         if (wl >= 0 && wl < per_cta && (wl & (HDB_CT - 1)) == tid) live &= ~(1u << (wl / HDB_CT));

@@ -501,7 +501,8 @@ int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32
     const int pt = (n + HDB_CS * HDB_CT - 1) / (HDB_CS * HDB_CT);
     if (pt <= HDB_PT_MAX && !(flags & LLCK_MST_SINGLE_CTA)) {
         const size_t smem = (size_t)pt * HDB_CT * sizeof(double4) + 2 * HDB_CS * sizeof(HdbCand);
-        if (cudaFuncSetAttribute(hdb_prim_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+        auto kern = (flags & LLCK_MST_DIM3) ? hdb_prim_cluster_kernel<true> : hdb_prim_cluster_kernel<false>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
             cudaLaunchConfig_t cfg = {};
             cudaLaunchAttribute attr[1];
             cfg.blockDim = dim3(HDB_CT); cfg.dynamicSmemBytes = smem; cfg.gridDim = dim3(nfits * HDB_CS); cfg.stream = st;
@@ -509,8 +510,8 @@ int llck_hdbscan_mst(const double* X, int32_t n, const double* core, const int32
             attr[0].val.clusterDim.x = HDB_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, hdb_prim_cluster_kernel, &cfg) == cudaSuccess && nclusters >= 1) {
-                CK(cudaLaunchKernelEx(&cfg, hdb_prim_cluster_kernel, X, (int)n, core, core_row, pt, (long long*)mst_src, (long long*)mst_dst, mst_w));
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters >= 1) {
+                CK(cudaLaunchKernelEx(&cfg, kern, X, (int)n, core, core_row, pt, (long long*)mst_src, (long long*)mst_dst, mst_w));
                 return 0;
             }
         }

@@ -380,6 +380,9 @@ def hdbscan_msts_device(features, min_samples_list, device=None, single_cta=Fals
         st = torch.cuda.current_stream(dev).cuda_stream
         _native.check_rc(lib.llck_hdbscan_core_distances(Xd.data_ptr(), n, kmax, core.data_ptr(), st), "llck_hdbscan_core_distances")
         rows = torch.tensor([int(k) - 1 for k in min_samples_list], dtype=torch.int32, device=dev)
+        mst_flags = _native.MST_SINGLE_CTA if single_cta else 0
+        if n and bool((X[:, 3] == X[0, 3]).all()):
+            mst_flags |= _native.MST_DIM3        # every point has the same 4th coordinate (the phase feature is zeroed): skip it, exactly
         mr = torch.empty((F, n), dtype=torch.float64, device=dev)
         cs = torch.empty((F, n), dtype=torch.int32, device=dev)
         src = torch.empty((F, n - 1), dtype=torch.int64, device=dev)
@@ -387,7 +390,7 @@ def hdbscan_msts_device(features, min_samples_list, device=None, single_cta=Fals
         w = torch.empty((F, n - 1), dtype=torch.float64, device=dev)
         _native.check_rc(lib.llck_hdbscan_mst(Xd.data_ptr(), n, core.data_ptr(), rows.data_ptr(), F, mr.data_ptr(), cs.data_ptr(),
                                               src.data_ptr(), dst.data_ptr(), w.data_ptr(),
-                                              _native.MST_SINGLE_CTA if single_cta else 0, st), "llck_hdbscan_mst")
+                                              mst_flags, st), "llck_hdbscan_mst")
         return src.cpu().numpy(), dst.cpu().numpy(), w.cpu().numpy()
 
 

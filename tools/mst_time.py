@@ -24,7 +24,7 @@ def timed(fn):
     e0.record(); fn(); e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)
 for rep in range(2):
     t_core = timed(lambda: lib.llck_hdbscan_core_distances(Xd.data_ptr(), n, kmax, core.data_ptr(), st))
-    t_cl = timed(lambda: lib.llck_hdbscan_mst(Xd.data_ptr(), n, core.data_ptr(), rows.data_ptr(), F, mr.data_ptr(), cs.data_ptr(), src.data_ptr(), dst.data_ptr(), w.data_ptr(), 0, st))
+    t_cl = timed(lambda: lib.llck_hdbscan_mst(Xd.data_ptr(), n, core.data_ptr(), rows.data_ptr(), F, mr.data_ptr(), cs.data_ptr(), src.data_ptr(), dst.data_ptr(), w.data_ptr(), 2, st))      # 2 = LLCK_MST_DIM3: the 4th coordinate is 0 for every point
     a = (src.clone(), dst.clone(), w.clone())
     t_1 = timed(lambda: lib.llck_hdbscan_mst(Xd.data_ptr(), n, core.data_ptr(), rows.data_ptr(), F, mr.data_ptr(), cs.data_ptr(), src.data_ptr(), dst.data_ptr(), w.data_ptr(), 1, st))
     same = bool((a[0] == src).all() and (a[1] == dst).all() and (a[2] == w).all())
