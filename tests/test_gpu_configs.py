@@ -506,3 +506,43 @@ def test_two_stream_schedule_for_a_ragged_partial_wave(cuda):
             dmu, dD = compare_members(res.mu[k, :m], res.D[k, :m], mu, D)
             assert dmu < TOL and dD < TOL, (k, dmu, dD)
         assert np.allclose(a.sing_vals[k, :m], info.singular_values, rtol=1e-8, atol=1e-12)
+
+
+def test_maximum_size_m2048_properties(cuda):
+    """The largest supported Hankel dimension (LLCK_M_MAX = 2048, N = 4096): singular values against LAPACK, generalized-eigen residual
+    of sampled poles, signal reconstruction -- the oracle's eig at this size would take a minute, the properties do not need it."""
+    from llckbdm_b200.ensemble import solve_ensemble
+    from oracle.kbdm_oracle import brain_sim, hankel_matrices
+    c = brain_sim(4096, 1e-3, 0)
+    m = 2048
+    res = solve_ensemble(c, [m], [m], 1, 0.0, DWELL)
+    assert res.status[0] == 0
+    U0, _, U1 = hankel_matrices(c, m, 1)
+    s_ref = np.linalg.svd(U0, compute_uv=False)
+    assert np.allclose(res.sing_vals[0], s_ref, rtol=1e-8, atol=1e-12)
+    mu, D = res.mu[0], res.D[0]
+    for k in (0, 1000, 2047):
+        smin = np.linalg.svd(U1 - mu[k] * U0, compute_uv=False)[-1]
+        assert smin < 1e-9 * s_ref[0]
+    n = np.arange(64)
+    recon = (D[None, :] * mu[None, :] ** n[:, None]).sum(axis=1)
+    assert np.abs(recon - c[:64]).max() < 1e-6 * np.abs(c).max()
+
+
+def test_empty_and_degenerate_ensembles(cuda):
+    """Empty m_range, a one-member ensemble, and members that all filter to nothing are handled like the reference does
+    (sampling.py:52-72: empty lists; empty members are dropped)."""
+    from llckbdm_b200.sampling import sample_kbdm, sample_kbdm_pooled
+    from llckbdm_b200.llckbdm import llc_kbdm
+    from oracle.kbdm_oracle import brain_sim
+    c = brain_sim(512, 1e-3, 3)
+    assert sample_kbdm(c, DWELL, [], p=1, l=None) == ([], [])
+    s, f = sample_kbdm_pooled(c, DWELL, [], p=1, l=None)
+    assert s.shape == (0, 4) and f.shape == (0, 4)
+    lls, infos = sample_kbdm(c, DWELL, [17], p=1, l=None)
+    assert len(lls) == 1 and infos[0].m == 17
+    tiny = 1e-9 * c                                         # every amplitude below the 1e-6 filter threshold: all members dropped
+    lls, infos = sample_kbdm(tiny, DWELL, [20, 30], p=1, l=None)
+    assert lls == [] and infos == []
+    r = llc_kbdm(tiny, DWELL, [20, 30, 40])
+    assert len(r.line_list) == 0 and r.rmse is None
