@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--members", type=int, default=1184, help="members of the fixed ensemble solved per step by the whole job (8 x 148)")
-    ap.add_argument("--m", type=int, default=1024)
+    ap.add_argument("--hankel-dim", dest="m", type=int, default=1024, help="Hankel dimension m = l of every member")
     ap.add_argument("--e2e-steps", type=int, default=3, help="steps of the end-to-end leg (host to host)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1..C5 / wave-boundary extras (N = 1 only)")

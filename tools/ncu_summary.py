@@ -42,7 +42,7 @@ for rep in sys.argv[2:]:
         json.dump({"kernel": "hqr_kernel", "m": 1024, "members_per_launch": grid,
                    "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                    "duration_ns_under_ncu": row[hdr.index("gpu__time_duration.sum")],
-                   "source": "ncu --set full capture " + os.path.basename(rep) + " (tools/ncu_pass.sh, bench --members 148 --m 1024)"},
+                   "source": "ncu --set full capture " + os.path.basename(rep) + " (tools/ncu_pass.sh, bench --members 148, m = 1024)"},
                   open(os.path.join(os.path.dirname(os.path.abspath(sys.argv[1])), "hqr_traffic.json"), "w"), indent=1)
 open(sys.argv[1], "w").write("\n".join(out) + "\n")
 print("\n".join(out))
