@@ -567,3 +567,18 @@ def test_llc_kbdm_matches_the_real_reference_driver_golden(cuda, name):
     assert np.allclose(got[:, :3], want[:, :3], rtol=1e-6, atol=0)
     assert np.allclose(got[:, 3], want[:, 3], atol=1e-8)
     assert res.rmse < 1e-9
+
+
+def test_truncated_rank_at_headline_size_m1024_l30(cuda):
+    """m = 1024 with only l = 30 singular triplets kept (the SVD-bound shape of BASELINE.md §2): poles, amplitudes and ALL 1024
+    singular values against the oracle."""
+    from llckbdm_b200.ensemble import solve_ensemble
+    from oracle.kbdm_oracle import brain_sim, compare_members, kbdm_oracle
+    c = brain_sim(2048, 1e-3, 0)
+    res = solve_ensemble(c, [1024], [30], 1, 0.0, DWELL)
+    assert res.status[0] == 0
+    _, info, mu, D = kbdm_oracle(c, DWELL, m=1024, l=30, return_mu=True)
+    dmu, dD = compare_members(res.mu[0, :30], res.D[0, :30], mu, D)
+    assert dmu < TOL and dD < TOL, (dmu, dD)
+    assert info.singular_values.shape == (1024,)
+    assert np.allclose(res.sing_vals[0], info.singular_values, rtol=1e-8, atol=1e-12)
