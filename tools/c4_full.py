@@ -32,6 +32,15 @@ for c0 in range(v_lo, v_hi, CH):
         out_ll[c0 - v_lo + idx] = r["line_lists"].cpu().numpy()
         bad += int((r["status"] != 0).sum().item())
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
+if world > 1:                                   # no exchange in the data path; only the clock is reduced (max over ranks)
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+    tt = torch.tensor([dt, float(bad)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt_max = float(tt[0]); bad_max = int(tt[1])
+    dist.destroy_process_group()
+else:
+    dt_max, bad_max = dt, bad
 if rank == 0:
     from oracle.kbdm_oracle import compare_members, kbdm_oracle, mu_from_line_list
     worst = 0.0
@@ -41,7 +50,7 @@ if rank == 0:
         dmu, dD = compare_members(mu_from_line_list(ll, 5e-4), ll[:, 0] * np.exp(1j * ll[:, 3]), mu, D)
         worst = max(worst, dmu, dD)
     nv = v_hi - v_lo
-    print(json.dumps({"config": "C4", "voxels_total": V, "n_gpus": world, "voxels_this_rank": nv, "seconds": dt, "of_which_input_synthesis_s": gen_s,
+    print(json.dumps({"config": "C4", "voxels_total": V, "n_gpus": world, "voxels_this_rank": nv, "seconds": dt, "seconds_max_over_ranks": dt_max, "voxels_per_s_whole_job": V / dt_max, "bad_status_max_over_ranks": bad_max, "of_which_input_synthesis_s": gen_s,
                       "voxels_per_s_per_gpu": nv / dt, "voxels_per_s_solve_only": nv / (dt - gen_s),
                       "frac_of_fp64_peak": nv * ensemble.flops_per_solve(512, 512) / (dt - gen_s) / 1e12 / 37.209,
                       "bad_status": bad, "sampled_parity_vs_oracle_3_voxels": worst, "chunk": CH}), flush=True)
