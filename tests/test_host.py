@@ -241,3 +241,31 @@ def test_native_labels_from_mst_reproduce_hdbscan_fit():
     tiny = X[:7]
     assert np.array_equal(L._fit_one(tiny, 50), HDBSCAN(min_samples=7, copy=True).fit(tiny).labels_)
     assert L._library_min_samples(50, 7) == 7 and L._library_min_samples(1, 100) == 2
+
+
+def test_hdbscan_labels_entry_validates_its_arguments(native_lib):
+    """llck_hdbscan_labels is host code: callable without a GPU.  Out-of-range nodes / permutations are bad arguments, a 2-point
+    tree gives all noise (min_cluster_size 5), and the thread count does not change the result."""
+    import ctypes
+    src = np.array([[0, 1, 2, 3, 4, 5, 6, 7, 8]], dtype=np.int64)
+    dst = src + 1
+    w = np.array([[1, 1, 1, 1, 9, 1, 1, 1, 1]], dtype=np.float64)
+    order = np.argsort(w, axis=1).astype(np.int64)
+
+    def run(src, dst, w, order, n, nthreads=0, mcs=5):
+        labels = np.full((1, n), 77, dtype=np.int32)
+        rc = native_lib.llck_hdbscan_labels(src.ctypes.data, dst.ctypes.data, w.ctypes.data, order.ctypes.data if order is not None else None,
+                                            n, 1, mcs, nthreads, labels.ctypes.data)
+        return rc, labels[0]
+
+    rc, lab = run(src, dst, w, order, 10)
+    assert rc == 0 and set(lab[:5]) == {lab[0]} and set(lab[5:]) == {lab[5]} and lab[0] != lab[5] and lab.min() == 0   # two chains of 5
+    rc1, lab1 = run(src, dst, w, order, 10, nthreads=1)
+    assert rc1 == 0 and np.array_equal(lab, lab1)
+    bad = src.copy(); bad[0, 3] = 10
+    assert run(bad, dst, w, order, 10)[0] == _native.E_BADARG
+    badorder = order.copy(); badorder[0, 0] = 9
+    assert run(src, dst, w, badorder, 10)[0] == _native.E_BADARG
+    assert run(src, dst, w, order, 10, mcs=1)[0] == _native.E_BADARG
+    rc, lab = run(src[:, :1], dst[:, :1], w[:, :1], None, 2)
+    assert rc == 0 and list(lab) == [-1, -1]
